@@ -1,0 +1,190 @@
+/*
+ * spmv_b200.h — C-ABI of the B200-native sparse SGEMV library (libspmv_b200.so).
+ *
+ * Operation (reference README.md:29-35, tester.cpp:36-45):
+ *     Y = X * A,  X: float[M],  A: float[M][N] row-major (A[j*N+i]),  Y: float[N]
+ *     y[i] = sum_j x[j] * A[j][i]
+ *
+ * The reference (PACTHEMAN123/spMV-test) has no FFI layer: its boundary is the
+ * C++ launcher set in src/include/kernel.hpp:8-17, each of which packs a dense
+ * host matrix, uploads, launches once, downloads and frees.  This header is the
+ * plan/handle API that sits underneath drop-in re-implementations of those
+ * launchers (spmv_test_b200/host/launchers.cpp) and that tests / bench.py bind
+ * with ctypes.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - every function returns 0 (SPMV_OK) or a negative spmv_status_t;
+ *     spmv_last_error() gives the message of the calling thread's last failure.
+ *     Nothing below the C++ shim calls exit() (the reference's CUDA_CHECK,
+ *     kernel.hpp:21-28, does; the shim keeps that behaviour).
+ *   - "d_" pointers are device pointers on the plan's device, "h_"/unprefixed
+ *     pointers are host pointers.  stream is a cudaStream_t passed as void*.
+ *   - spmv_run() is asynchronous, allocation-free and CUDA-graph capturable.
+ *   - results are deterministic: no floating-point atomics anywhere.
+ *   - there is no CPU fallback: if no CUDA device is usable the call fails.
+ */
+#ifndef SPMV_B200_H
+#define SPMV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPMV_B200_ABI_VERSION 1
+
+typedef enum spmv_status {
+    SPMV_OK            =  0,
+    SPMV_ERR_ARG       = -1,  /* null pointer, bad enum, bad option            */
+    SPMV_ERR_SHAPE     = -2,  /* shape precondition violated (see below)       */
+    SPMV_ERR_CUDA      = -3,  /* a CUDA runtime call failed                    */
+    SPMV_ERR_NOMEM     = -4,  /* host allocation failed                        */
+    SPMV_ERR_UNSUPPORTED = -5 /* valid request this build cannot serve         */
+} spmv_status_t;
+
+/*
+ * Variants.  Each replaces one launcher family of the reference:
+ *   SPMV_WSP   weight-sparse       wsp_gemv_gpu / csr_naive_gemv_gpu   (kernel.hpp:11,13; wsp.cu:4-138; csr_naive.cu:6-23)
+ *   SPMV_ASP   activation-sparse   asp_gemv_gpu                        (kernel.hpp:14; asp.cu:6-211)
+ *   SPMV_AWSP  both                awsp_gemv_gpu / awsp_ref_gemv_gpu   (kernel.hpp:15-16; awsp.cu:5-317; awsp_ref.cu:6-185)
+ *   SPMV_TCSR  tiled bitmap-CSR    csr_tiling_gemv_gpu                 (kernel.hpp:12; csr_tiling.cu:24-114)
+ */
+typedef enum spmv_variant {
+    SPMV_WSP  = 0,
+    SPMV_ASP  = 1,
+    SPMV_AWSP = 2,
+    SPMV_TCSR = 3
+} spmv_variant_t;
+
+/* Tuning knobs; zero-initialise for defaults.  struct_size must be sizeof(spmv_options_t). */
+typedef struct spmv_options {
+    uint32_t struct_size;
+    int32_t  row_splits;     /* asp/awsp/tcsr: CTAs along M per column tile (0 = auto)   */
+    int32_t  warps_per_col;  /* wsp: warps cooperating on one column, 1/2/4/8 (0 = auto) */
+    int32_t  index_bits;     /* wsp: 16 or 32 bit row indices (0 = auto: 16 if M<65536)  */
+    int32_t  reserved[4];
+} spmv_options_t;
+
+typedef struct spmv_plan spmv_plan_t;   /* opaque */
+
+typedef struct spmv_plan_info {
+    int32_t  variant;
+    int64_t  M, N;
+    int64_t  nnz;               /* stored non-zeros (A != 0.0f); M*N for asp                */
+    int64_t  device_bytes;      /* bytes of the packed format resident in HBM               */
+    int64_t  scratch_bytes;     /* split partial sums + counters                             */
+    int32_t  kernels_per_run;   /* kernel launches one spmv_run() issues                     */
+    int32_t  grid_x, grid_y, block; /* launch geometry of the main kernel                    */
+    int32_t  smem_bytes;        /* dynamic shared memory of the main kernel                  */
+    int32_t  index_bits;        /* wsp only                                                  */
+    int32_t  row_splits;
+    int32_t  warps_per_col;
+} spmv_plan_info_t;
+
+/* ---- library ----------------------------------------------------------------------------- */
+int         spmv_abi_version(void);
+const char *spmv_last_error(void);
+/* Number of CUDA devices visible, or a negative status.  Never throws, never exits. */
+int         spmv_device_count(void);
+
+/* ---- plans ------------------------------------------------------------------------------- */
+/*
+ * Pack a dense row-major host matrix (leading dimension lda >= N, so a column
+ * slab of a wider matrix can be passed as A + col_begin with lda = N_total —
+ * the multi-GPU partitioner does exactly that) into the variant's device format
+ * and upload it to the current CUDA device.  Replaces the pack+cudaMalloc+H2D
+ * prologue every reference launcher repeats (e.g. awsp.cu:323-344).
+ *
+ * Preconditions (reference tester.cpp:9-10 asserts M%32==0 && N%32==0; its kernels
+ * silently need more): here M >= 0 is arbitrary, N % 32 == 0 is
+ * required and anything else is rejected with SPMV_ERR_SHAPE.  M*N == 0 is legal.
+ * A weight is "zero" iff value == 0.0f is true (so -0.0f is zero, NaN is kept):
+ * matrix_csr.cpp:15, wsp.cpp:17, awsp.cpp:20.
+ */
+int spmv_plan_create_dense(int variant, int64_t M, int64_t N, const float *A, int64_t lda,
+                           const spmv_options_t *opts, spmv_plan_t **out);
+
+/*
+ * Direct-to-sparse construction for shapes whose dense form cannot exist
+ * (BASELINE configs 4 and 5).  Input is the reference CSRMatrix orientation
+ * (matrix_csr.cpp:8-22: one list per OUTPUT column i, entries (row j, value) with
+ * j ascending) but with 64-bit pointers and the N+1 sentinel the reference omits.
+ * Supported for SPMV_WSP, SPMV_AWSP and SPMV_TCSR.
+ */
+int spmv_plan_create_csc(int variant, int64_t M, int64_t N, const int64_t *col_ptr,
+                         const int32_t *row_idx, const float *values,
+                         const spmv_options_t *opts, spmv_plan_t **out);
+
+int  spmv_plan_info(const spmv_plan_t *plan, spmv_plan_info_t *info);
+void spmv_plan_destroy(spmv_plan_t *plan);
+
+/*
+ * Bytes one call moves for a given activation vector (host copy of x):
+ *   alg_bytes  — the format-independent figure of SURVEY §8d:
+ *                8*nnz_t + 4*(N+1) + 4*M + 4*N   (wsp/tcsr: nnz_t = all stored nnz;
+ *                awsp: stored nnz in rows with x[j] != 0),  asp: 4*M_nz*N + 4*M + 4*N
+ *   phys_bytes — bytes of the packed arrays the kernel actually has to read for
+ *                this x in this library's format, plus x and y.
+ */
+int spmv_plan_traffic(const spmv_plan_t *plan, const float *x, double *alg_bytes,
+                      double *phys_bytes, int64_t *nnz_touched);
+
+/* ---- execution --------------------------------------------------------------------------- */
+/* y = x*A on device buffers (x: M floats, y: N floats; 16-byte aligned). */
+int spmv_run(spmv_plan_t *plan, const float *d_x, float *d_y, void *stream);
+
+/*
+ * Host-buffer convenience: H2D x, run, D2H y, synchronise — the per-call part of a
+ * reference launcher once the matrix is resident (awsp.cu:342-381).  If timing_ms is
+ * non-NULL it receives the device time of the kernel(s) alone (the region the
+ * reference's TIME_KERNEL macro brackets, kernel.hpp:31-48).
+ */
+int spmv_run_host(spmv_plan_t *plan, const float *x, float *y, float *timing_ms);
+
+/*
+ * Activation compaction (the x != 0.0f test of asp.cu:23, awsp.cu:98,127,228,258,
+ * awsp_ref.cu:52,96, made an explicit pass): writes the ascending list of rows j
+ * with x[j] != 0.0f, their values, and the count.  d_idx/d_val need M entries.
+ * Deterministic and bit-exact with the oracle.
+ */
+int spmv_compact_x(const float *d_x, int64_t M, int32_t *d_idx, float *d_val,
+                   int32_t *d_count, void *stream);
+
+/* ---- reference host layouts (CPU only; used by the drop-in format classes) ----------------- */
+/*
+ * Bit-exact re-implementations of the reference's six host packers.  No GPU needed.
+ *   layout                 i32_a                 i32_b        u32        f32          aux
+ *   SPMV_LAYOUT_CSR        row_pointers[N]       col_idx[nnz] -          values[nnz]  -              matrix_csr.cpp:5-23
+ *   SPMV_LAYOUT_TCSR       blk_idx[(M/32)(N/32)+1] -          bitmaps    values[nnz]  -              tcsr.cpp:5-38
+ *   SPMV_LAYOUT_WSP        -                     -            bitmaps    values       nz_max_m, nz_max_n   wsp.cpp:3-40
+ *   SPMV_LAYOUT_ASP        -                     -            -          values[M*N]  -              asp.cpp:3-14
+ *   SPMV_LAYOUT_AWSP       -                     -            bitmaps    values       nz_bk_max      awsp.cpp:3-49
+ *   SPMV_LAYOUT_AWSP_REF   warp_nz_offset[4]     -            bitmaps    values       -              awsp_ref.cpp:4-58
+ * Shape rule: M % 32 == 0 and N % 32 == 0 (tester.cpp:9-10); AWSP_REF also M % 4 == 0.
+ */
+typedef enum spmv_layout {
+    SPMV_LAYOUT_CSR = 0,
+    SPMV_LAYOUT_TCSR = 1,
+    SPMV_LAYOUT_WSP = 2,
+    SPMV_LAYOUT_ASP = 3,
+    SPMV_LAYOUT_AWSP = 4,
+    SPMV_LAYOUT_AWSP_REF = 5
+} spmv_layout_t;
+
+typedef struct spmv_ref_packed {
+    int32_t  *i32_a;  int64_t n_i32_a;
+    int32_t  *i32_b;  int64_t n_i32_b;
+    uint32_t *u32;    int64_t n_u32;
+    float    *f32;    int64_t n_f32;
+    int32_t   aux[4];
+} spmv_ref_packed_t;
+
+int  spmv_ref_pack(int layout, int M, int N, const float *A, spmv_ref_packed_t *out);
+void spmv_ref_packed_free(spmv_ref_packed_t *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPMV_B200_H */
