@@ -35,6 +35,12 @@ extern "C" {
 
 #define SPMV_B200_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define SPMV_API __attribute__((visibility("default")))
+#else
+#define SPMV_API
+#endif
+
 typedef enum spmv_status {
     SPMV_OK            =  0,
     SPMV_ERR_ARG       = -1,  /* null pointer, bad enum, bad option            */
@@ -64,7 +70,8 @@ typedef struct spmv_options {
     int32_t  row_splits;     /* asp/awsp/tcsr: CTAs along M per column tile (0 = auto)   */
     int32_t  warps_per_col;  /* wsp: warps cooperating on one column, 1/2/4/8 (0 = auto) */
     int32_t  index_bits;     /* wsp: 16 or 32 bit row indices (0 = auto: 16 if M<65536)  */
-    int32_t  reserved[4];
+    int32_t  slab_cols;      /* awsp/tcsr: columns per slab, power of two 256..4096 (0 = auto from density) */
+    int32_t  reserved[3];
 } spmv_options_t;
 
 typedef struct spmv_plan spmv_plan_t;   /* opaque */
@@ -81,13 +88,15 @@ typedef struct spmv_plan_info {
     int32_t  index_bits;        /* wsp only                                                  */
     int32_t  row_splits;
     int32_t  warps_per_col;
+    int32_t  slab_cols;         /* awsp/tcsr                                                 */
+    int32_t  reserved[3];
 } spmv_plan_info_t;
 
 /* ---- library ----------------------------------------------------------------------------- */
-int         spmv_abi_version(void);
-const char *spmv_last_error(void);
+SPMV_API int         spmv_abi_version(void);
+SPMV_API const char *spmv_last_error(void);
 /* Number of CUDA devices visible, or a negative status.  Never throws, never exits. */
-int         spmv_device_count(void);
+SPMV_API int         spmv_device_count(void);
 
 /* ---- plans ------------------------------------------------------------------------------- */
 /*
@@ -103,7 +112,7 @@ int         spmv_device_count(void);
  * A weight is "zero" iff value == 0.0f is true (so -0.0f is zero, NaN is kept):
  * matrix_csr.cpp:15, wsp.cpp:17, awsp.cpp:20.
  */
-int spmv_plan_create_dense(int variant, int64_t M, int64_t N, const float *A, int64_t lda,
+SPMV_API int spmv_plan_create_dense(int variant, int64_t M, int64_t N, const float *A, int64_t lda,
                            const spmv_options_t *opts, spmv_plan_t **out);
 
 /*
@@ -113,12 +122,19 @@ int spmv_plan_create_dense(int variant, int64_t M, int64_t N, const float *A, in
  * j ascending) but with 64-bit pointers and the N+1 sentinel the reference omits.
  * Supported for SPMV_WSP, SPMV_AWSP and SPMV_TCSR.
  */
-int spmv_plan_create_csc(int variant, int64_t M, int64_t N, const int64_t *col_ptr,
+SPMV_API int spmv_plan_create_csc(int variant, int64_t M, int64_t N, const int64_t *col_ptr,
                          const int32_t *row_idx, const float *values,
                          const spmv_options_t *opts, spmv_plan_t **out);
 
-int  spmv_plan_info(const spmv_plan_t *plan, spmv_plan_info_t *info);
-void spmv_plan_destroy(spmv_plan_t *plan);
+SPMV_API int  spmv_plan_info(const spmv_plan_t *plan, spmv_plan_info_t *info);
+SPMV_API void spmv_plan_destroy(spmv_plan_t *plan);
+
+/*
+ * Device-side copy of a plan (same device): a second, independent resident copy of the packed
+ * matrix.  The benchmark rotates over clones whose total size exceeds the L2 so that every
+ * timed call streams from HBM; a server would use it to replicate a hot matrix.
+ */
+SPMV_API int spmv_plan_clone(const spmv_plan_t *plan, spmv_plan_t **out);
 
 /*
  * Bytes one call moves for a given activation vector (host copy of x):
@@ -128,12 +144,12 @@ void spmv_plan_destroy(spmv_plan_t *plan);
  *   phys_bytes — bytes of the packed arrays the kernel actually has to read for
  *                this x in this library's format, plus x and y.
  */
-int spmv_plan_traffic(const spmv_plan_t *plan, const float *x, double *alg_bytes,
+SPMV_API int spmv_plan_traffic(const spmv_plan_t *plan, const float *x, double *alg_bytes,
                       double *phys_bytes, int64_t *nnz_touched);
 
 /* ---- execution --------------------------------------------------------------------------- */
 /* y = x*A on device buffers (x: M floats, y: N floats; 16-byte aligned). */
-int spmv_run(spmv_plan_t *plan, const float *d_x, float *d_y, void *stream);
+SPMV_API int spmv_run(spmv_plan_t *plan, const float *d_x, float *d_y, void *stream);
 
 /*
  * Host-buffer convenience: H2D x, run, D2H y, synchronise — the per-call part of a
@@ -141,7 +157,7 @@ int spmv_run(spmv_plan_t *plan, const float *d_x, float *d_y, void *stream);
  * non-NULL it receives the device time of the kernel(s) alone (the region the
  * reference's TIME_KERNEL macro brackets, kernel.hpp:31-48).
  */
-int spmv_run_host(spmv_plan_t *plan, const float *x, float *y, float *timing_ms);
+SPMV_API int spmv_run_host(spmv_plan_t *plan, const float *x, float *y, float *timing_ms);
 
 /*
  * Activation compaction (the x != 0.0f test of asp.cu:23, awsp.cu:98,127,228,258,
@@ -149,8 +165,22 @@ int spmv_run_host(spmv_plan_t *plan, const float *x, float *y, float *timing_ms)
  * with x[j] != 0.0f, their values, and the count.  d_idx/d_val need M entries.
  * Deterministic and bit-exact with the oracle.
  */
-int spmv_compact_x(const float *d_x, int64_t M, int32_t *d_idx, float *d_val,
-                   int32_t *d_count, void *stream);
+SPMV_API int    spmv_compact_x(const float *d_x, int64_t M, int32_t *d_idx, float *d_val,
+                      int32_t *d_count, void *d_scratch, size_t scratch_bytes, void *stream);
+/* Device scratch spmv_compact_x needs for this M (0 for M <= 32768: d_scratch may be NULL). */
+SPMV_API size_t spmv_compact_x_scratch_bytes(int64_t M);
+
+/* ---- multi-GPU partitioner (host only) --------------------------------------------------- */
+/*
+ * Column-slab partition of the N outputs over `parts` GPUs (BASELINE config 5; the reference
+ * is single-GPU): bounds[g] .. bounds[g+1] is the contiguous range GPU g owns.
+ * Boundaries are multiples of `align` (use the slab width, >= 32).  With col_ptr == NULL the
+ * split is by column count; with a CSR(A^T) col_ptr (N+1 entries) it is balanced by
+ * non-zeros.  Every GPU then runs the single-GPU kernel on its slab and the Y slices are
+ * joined by one all-gather; no reduction crosses GPUs, so results stay deterministic.
+ */
+SPMV_API int spmv_partition_columns(int64_t N, int parts, int64_t align, const int64_t *col_ptr,
+                           int64_t *bounds /* parts+1 */);
 
 /* ---- reference host layouts (CPU only; used by the drop-in format classes) ----------------- */
 /*
@@ -181,8 +211,8 @@ typedef struct spmv_ref_packed {
     int32_t   aux[4];
 } spmv_ref_packed_t;
 
-int  spmv_ref_pack(int layout, int M, int N, const float *A, spmv_ref_packed_t *out);
-void spmv_ref_packed_free(spmv_ref_packed_t *p);
+SPMV_API int  spmv_ref_pack(int layout, int M, int N, const float *A, spmv_ref_packed_t *out);
+SPMV_API void spmv_ref_packed_free(spmv_ref_packed_t *p);
 
 #ifdef __cplusplus
 }

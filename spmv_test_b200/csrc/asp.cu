@@ -1,0 +1,147 @@
+// asp.cu — activation-sparse SGEMV on a dense row-major A.
+//
+// Replaces asp_kernel_v0/v1/v2 (reference asp.cu:6-211).  The reference re-tiles A into
+// 32x32 tiles (asp.cpp:3-14), gives each 32-column slab to a 4-warp CTA and tests x[j] != 0
+// in the inner loop, one 128-byte tile row per warp load.  Here A stays row-major (a row is
+// one contiguous N*4-byte run), and
+//   * a CTA owns (512-column tile, row range); it first compacts its slice of x into a
+//     shared-memory list of (row, x[row]) with x[row] != 0.0f (asp.cu:23's test, made a pass:
+//     ballot + popc prefix, order preserving), so inactive rows are never addressed;
+//   * every thread owns four adjacent output columns and streams the active rows with
+//     128-bit loads, kAspUnroll rows in flight (a warp reads 512 contiguous bytes per row);
+//   * row splits are summed in split order by the last CTA to arrive (integer ticket).
+// Deterministic, no floating-point atomics.
+#include <algorithm>
+
+#include "common.cuh"
+#include "plan.hpp"
+
+namespace spmv {
+
+namespace {
+
+constexpr int kAspThreads = 128;
+constexpr int kAspTile = kAspThreads * 4;     // output columns per CTA
+constexpr int kAspChunk = 1024;               // rows compacted per pass
+constexpr int kAspUnroll = 8;
+
+__global__ void __launch_bounds__(kAspThreads)
+asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ x, float *__restrict__ y,
+           float *__restrict__ partial, unsigned *__restrict__ tickets, int M, int N, int rows_per_split,
+           int splits)
+{
+    __shared__ int rows_s[kAspChunk];
+    __shared__ float xs_s[kAspChunk];
+    __shared__ int wcnt[kAspThreads / 32];
+    __shared__ int last_flag;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x, split = blockIdx.y;
+    const int c0 = tile * kAspTile + tid * 4;
+    const bool col_ok = c0 < N;                           // N % 4 == 0: all four or none
+    const int r_begin = split * rows_per_split;
+    const int r_end = min(M, r_begin + rows_per_split);
+    const float *Ac = A + c0;
+
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r0 = r_begin; r0 < r_end; r0 += kAspChunk) {
+        // ---- compaction of x[r0 .. r0+chunk): warp w takes a contiguous quarter ----------------
+        constexpr int kSpan = kAspChunk / (kAspThreads / 32);   // 256 rows per warp
+        constexpr int kSteps = kSpan / 32;                      // 8
+        float xr[kSteps]; unsigned bal[kSteps];
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < kSteps; k++) {
+            const int row = r0 + warp * kSpan + k * 32 + lane;
+            xr[k] = row < r_end ? __ldg(x + row) : 0.0f;
+            bal[k] = __ballot_sync(kFull, xr[k] != 0.0f);
+            cnt += __popc(bal[k]);
+        }
+        __syncthreads();                                  // previous chunk's list fully consumed
+        if (lane == 0) wcnt[warp] = cnt;
+        __syncthreads();
+        int base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kAspThreads / 32; w++) {
+            const int cw = wcnt[w];
+            if (w < warp) base += cw;
+            total += cw;
+        }
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int k = 0; k < kSteps; k++) {
+            if (xr[k] != 0.0f) {
+                const int pos = base + __popc(bal[k] & lt);
+                rows_s[pos] = r0 + warp * kSpan + k * 32 + lane;
+                xs_s[pos] = xr[k];
+            }
+            base += __popc(bal[k]);
+        }
+        __syncthreads();
+
+        // ---- stream the active rows ------------------------------------------------------------
+        if (col_ok) {
+            for (int i = 0; i < total; i += kAspUnroll) {
+                float4 a[kAspUnroll];
+#pragma unroll
+                for (int u = 0; u < kAspUnroll; u++) {
+                    if (i + u < total)
+                        a[u] = ldg_stream_f4(reinterpret_cast<const float4 *>(Ac + (long long)rows_s[i + u] * ld));
+                    else
+                        a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < kAspUnroll; u++) {
+                    const float xv = (i + u < total) ? xs_s[i + u] : 0.0f;
+                    acc.x = fmaf(a[u].x, xv, acc.x); acc.y = fmaf(a[u].y, xv, acc.y);
+                    acc.z = fmaf(a[u].z, xv, acc.z); acc.w = fmaf(a[u].w, xv, acc.w);
+                }
+            }
+        }
+    }
+
+    if (splits == 1) {
+        if (col_ok) *reinterpret_cast<float4 *>(y + c0) = acc;
+        return;
+    }
+    const size_t npad = (size_t)gridDim.x * kAspTile;
+    *reinterpret_cast<float4 *>(partial + (size_t)split * npad + (size_t)tile * kAspTile + tid * 4) = acc;
+    const int n_valid = min(kAspTile, N - tile * kAspTile);
+    split_reduce_finish(y, partial, tickets, tile, splits, kAspTile, n_valid, npad, &last_flag);
+}
+
+} // namespace
+
+int launch_asp(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st)
+{
+    if (p->N == 0) return SPMV_OK;
+    asp_kernel<<<p->grid, kAspThreads, 0, st>>>(p->asp.A, (long long)p->asp.ld, d_x, d_y, p->partial, p->tickets,
+                                               (int)p->M, (int)p->N, p->asp.rows_per_split, p->row_splits);
+    SPMV_CUDA(cudaGetLastError());
+    return SPMV_OK;
+}
+
+// grid = (ceil(N/512), row splits): about four CTAs per SM, at least 64 rows per split.
+int configure_asp(spmv_plan *p, const spmv_options_t *o)
+{
+    p->block = kAspThreads;
+    p->smem = 0;
+    p->tile_width = kAspTile;
+    p->col_tiles = (int)((p->N + kAspTile - 1) / kAspTile);
+    p->asp.tile_cols = kAspTile;
+    p->kernels_per_run = 1;
+    const int64_t M = std::max<int64_t>(p->M, 1);
+    int splits;
+    if (o && o->row_splits > 0) splits = (int)std::min<int64_t>(o->row_splits, M);
+    else splits = std::max(1, (4 * p->sm_count + p->col_tiles - 1) / std::max(1, p->col_tiles));
+    int rps = (int)((M + splits - 1) / splits);
+    if (!(o && o->row_splits > 0)) rps = std::max(64, rps);
+    rps = (rps + 31) / 32 * 32;
+    splits = (int)((M + rps - 1) / rps);
+    p->asp.rows_per_split = rps;
+    p->row_splits = splits;
+    p->grid = dim3((unsigned)std::max(1, p->col_tiles), (unsigned)splits, 1);
+    return alloc_split_scratch(p);
+}
+
+} // namespace spmv

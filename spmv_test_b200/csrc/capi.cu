@@ -1,0 +1,411 @@
+// capi.cu — the C-ABI of libspmv_b200.so (include/spmv_b200.h): plan life cycle, execution,
+// traffic accounting, error reporting.  No CPU compute path exists here: every entry point
+// that produces y launches the sm_100a kernels or fails.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "plan.hpp"
+
+namespace spmv {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_error(cudaError_t e, const char *what)
+{
+    cudaGetLastError();   // clear the sticky non-fatal error state
+    return set_error(SPMV_ERR_CUDA, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+}
+
+// every device allocation of a plan is registered here so destroy/clone stay generic
+struct DevBuf { size_t slot; size_t bytes; };
+struct PlanBufs { std::vector<DevBuf> v; };
+
+static PlanBufs *bufs(spmv_plan *p) { return reinterpret_cast<PlanBufs *>(p->bufs); }
+
+template <class T> static int dev_alloc(spmv_plan *p, T **slot, size_t count, bool zero)
+{
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    SPMV_CUDA(cudaMalloc(reinterpret_cast<void **>(slot), bytes));
+    if (zero) SPMV_CUDA(cudaMemset(*slot, 0, bytes));
+    bufs(p)->v.push_back({(size_t)(reinterpret_cast<char *>(slot) - reinterpret_cast<char *>(p)), bytes});
+    return SPMV_OK;
+}
+
+template <class T> static int upload(spmv_plan *p, T **slot, const std::vector<T> &h)
+{
+    int rc = dev_alloc(p, slot, h.size(), false);
+    if (rc) return rc;
+    if (!h.empty()) SPMV_CUDA(cudaMemcpy(*slot, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    p->device_bytes += (int64_t)(h.size() * sizeof(T));
+    return SPMV_OK;
+}
+
+int alloc_split_scratch(spmv_plan *p)
+{
+    if (p->row_splits <= 1) return SPMV_OK;
+    const size_t npad = (size_t)p->col_tiles * p->tile_width;
+    int rc = dev_alloc(p, &p->partial, npad * p->row_splits, false);
+    if (rc) return rc;
+    rc = dev_alloc(p, &p->tickets, (size_t)p->col_tiles, true);
+    if (rc) return rc;
+    p->scratch_bytes += (int64_t)(npad * p->row_splits * sizeof(float) + (size_t)p->col_tiles * sizeof(unsigned));
+    return SPMV_OK;
+}
+
+static int plan_begin(int variant, int64_t M, int64_t N, spmv_plan **out)
+{
+    if (!out) return set_error(SPMV_ERR_ARG, "null output pointer");
+    *out = nullptr;
+    if (variant < SPMV_WSP || variant > SPMV_TCSR) return set_error(SPMV_ERR_ARG, "unknown variant %d", variant);
+    if (M < 0 || N < 0) return set_error(SPMV_ERR_SHAPE, "negative shape %lld x %lld", (long long)M, (long long)N);
+    if (N % 32) return set_error(SPMV_ERR_SHAPE, "N = %lld is not a multiple of 32 (tester.cpp:9-10)", (long long)N);
+    if (M > INT32_MAX - 64 || N > INT32_MAX - 8192)
+        return set_error(SPMV_ERR_SHAPE, "shape %lld x %lld exceeds 32-bit row/column ids", (long long)M, (long long)N);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_error(SPMV_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)",
+                         e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    spmv_plan *p = new (std::nothrow) spmv_plan();
+    if (!p) return set_error(SPMV_ERR_NOMEM, "out of host memory");
+    p->bufs = new (std::nothrow) PlanBufs();
+    p->variant = variant; p->M = M; p->N = N;
+    if (cudaGetDevice(&p->device) != cudaSuccess) { cudaGetLastError(); p->device = 0; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, p->device) == cudaSuccess) {
+        p->sm_count = prop.multiProcessorCount;
+        p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    } else cudaGetLastError();
+    *out = p;
+    return SPMV_OK;
+}
+
+static int plan_finish(spmv_plan *p)
+{
+    int rc = dev_alloc(p, &p->d_x, (size_t)p->M + 4, true);
+    if (!rc) rc = dev_alloc(p, &p->d_y, (size_t)p->N + 4, true);
+    if (rc) return rc;
+    SPMV_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    SPMV_CUDA(cudaEventCreate(&p->ev0));
+    SPMV_CUDA(cudaEventCreate(&p->ev1));
+    SPMV_CUDA(cudaDeviceSynchronize());
+    return SPMV_OK;
+}
+
+static int setup_wsp(spmv_plan *p, const HostWsp &w, const spmv_options_t *o)
+{
+    p->nnz = w.nnz; p->fmt_groups = w.groups;
+    int rc = upload(p, &p->wsp.colptr, w.colptr);
+    if (!rc) rc = upload(p, &p->wsp.vals, w.vals);
+    if (!rc) {
+        if (w.index_bits == 16) rc = upload(p, reinterpret_cast<uint16_t **>(&p->wsp.idx), w.idx16);
+        else rc = upload(p, reinterpret_cast<uint32_t **>(&p->wsp.idx), w.idx32);
+    }
+    if (!rc) rc = configure_wsp(p, w, o);
+    return rc;
+}
+
+static int setup_panel(spmv_plan *p, HostPanel &h, const spmv_options_t *o)
+{
+    p->nnz = h.nnz; p->fmt_groups = h.groups;
+    int rc = upload(p, &p->panel.off, h.off);
+    p->off_bytes = (int64_t)h.off.size() * 4 + (int64_t)h.rel.size() * 2;
+    if (!rc && h.tiled) rc = upload(p, &p->panel.rel, h.rel);
+    if (!rc) rc = upload(p, &p->panel.vals, h.vals);
+    if (!rc) {
+        if (h.index_bits == 8) rc = upload(p, reinterpret_cast<uint8_t **>(&p->panel.idx), h.idx8);
+        else rc = upload(p, reinterpret_cast<uint16_t **>(&p->panel.idx), h.idx16);
+    }
+    if (!rc) rc = configure_panel(p, h, o);
+    p->row_nnz.swap(h.row_nnz); p->row_groups.swap(h.row_groups); p->row_segs.swap(h.row_segs);
+    return rc;
+}
+
+static bool opts_ok(const spmv_options_t *o)
+{
+    if (!o) return true;
+    if (o->struct_size != sizeof(spmv_options_t)) return false;
+    if (o->row_splits < 0 || o->warps_per_col < 0) return false;
+    if (o->index_bits != 0 && o->index_bits != 16 && o->index_bits != 32) return false;
+    if (o->slab_cols != 0 && (o->slab_cols < kMinSlabCols || o->slab_cols > kMaxSlabCols || (o->slab_cols & (o->slab_cols - 1))))
+        return false;
+    return true;
+}
+
+} // namespace spmv
+
+using namespace spmv;
+
+extern "C" {
+
+int spmv_abi_version(void) { return SPMV_B200_ABI_VERSION; }
+
+const char *spmv_last_error(void) { return g_err; }
+
+int spmv_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return 0;
+        return cuda_error(e, "cudaGetDeviceCount");
+    }
+    return n;
+}
+
+void spmv_plan_destroy(spmv_plan_t *p)
+{
+    if (!p) return;
+    if (p->bufs) {
+        for (const DevBuf &b : bufs(p)->v) {
+            void **slot = reinterpret_cast<void **>(reinterpret_cast<char *>(p) + b.slot);
+            if (*slot) cudaFree(*slot);
+        }
+        delete bufs(p);
+    }
+    destroy_wsp_state(p);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    cudaGetLastError();
+    delete p;
+}
+
+int spmv_plan_create_dense(int variant, int64_t M, int64_t N, const float *A, int64_t lda,
+                           const spmv_options_t *opts, spmv_plan_t **out)
+{
+    if (!opts_ok(opts)) return set_error(SPMV_ERR_ARG, "bad spmv_options_t");
+    if (!A && M * N > 0) return set_error(SPMV_ERR_ARG, "A is null");
+    if (lda < N) return set_error(SPMV_ERR_ARG, "lda %lld < N %lld", (long long)lda, (long long)N);
+    spmv_plan *p = nullptr;
+    int rc = plan_begin(variant, M, N, &p);
+    if (rc) return rc;
+    try {
+        if (variant == SPMV_WSP) {
+            HostWsp w;
+            rc = pack_wsp_dense(M, N, A, lda, opts ? opts->index_bits : 0, w);
+            if (rc) set_error(rc, "wsp: cannot pack (index width / size limits)");
+            else rc = setup_wsp(p, w, opts);
+        } else if (variant == SPMV_ASP) {
+            p->nnz = M * N;
+            p->asp.ld = N;
+            rc = dev_alloc(p, &p->asp.A, (size_t)M * N, false);
+            if (!rc && M * N > 0) {
+                cudaError_t e = cudaMemcpy2D(p->asp.A, (size_t)N * 4, A, (size_t)lda * 4, (size_t)N * 4, (size_t)M,
+                                             cudaMemcpyHostToDevice);
+                if (e != cudaSuccess) rc = cuda_error(e, "cudaMemcpy2D(A)");
+            }
+            p->device_bytes += M * N * 4;
+            if (!rc) rc = configure_asp(p, opts);
+        } else {
+            HostPanel h;
+            rc = pack_panel_dense(M, N, A, lda, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h);
+            if (rc) set_error(rc, "panel: cannot pack (size limits)");
+            else rc = setup_panel(p, h, opts);
+        }
+        if (!rc) rc = plan_finish(p);
+    } catch (const std::bad_alloc &) {
+        rc = set_error(SPMV_ERR_NOMEM, "out of host memory while packing");
+    }
+    if (rc) { spmv_plan_destroy(p); return rc; }
+    *out = p;
+    return SPMV_OK;
+}
+
+int spmv_plan_create_csc(int variant, int64_t M, int64_t N, const int64_t *col_ptr,
+                         const int32_t *row_idx, const float *values,
+                         const spmv_options_t *opts, spmv_plan_t **out)
+{
+    if (!opts_ok(opts)) return set_error(SPMV_ERR_ARG, "bad spmv_options_t");
+    if (variant == SPMV_ASP) return set_error(SPMV_ERR_UNSUPPORTED, "asp needs a dense matrix");
+    if (!col_ptr) return set_error(SPMV_ERR_ARG, "col_ptr is null");
+    if (N > 0 && col_ptr[N] > col_ptr[0] && (!row_idx || !values)) return set_error(SPMV_ERR_ARG, "null row_idx/values");
+    for (int64_t i = 0; i < N; i++)
+        if (col_ptr[i + 1] < col_ptr[i]) return set_error(SPMV_ERR_ARG, "col_ptr is not monotone at %lld", (long long)i);
+    spmv_plan *p = nullptr;
+    int rc = plan_begin(variant, M, N, &p);
+    if (rc) return rc;
+    try {
+        if (variant == SPMV_WSP) {
+            HostWsp w;
+            rc = pack_wsp_csc(M, N, col_ptr, row_idx, values, opts ? opts->index_bits : 0, w);
+            if (rc) set_error(rc, "wsp: cannot pack (row index out of range, index width or size limits)");
+            else rc = setup_wsp(p, w, opts);
+        } else {
+            HostPanel h;
+            rc = pack_panel_csc(M, N, col_ptr, row_idx, values, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h);
+            if (rc) set_error(rc, "panel: cannot pack (row index out of range or size limits)");
+            else rc = setup_panel(p, h, opts);
+        }
+        if (!rc) rc = plan_finish(p);
+    } catch (const std::bad_alloc &) {
+        rc = set_error(SPMV_ERR_NOMEM, "out of host memory while packing");
+    }
+    if (rc) { spmv_plan_destroy(p); return rc; }
+    *out = p;
+    return SPMV_OK;
+}
+
+int spmv_plan_clone(const spmv_plan_t *src, spmv_plan_t **out)
+{
+    if (!src || !out) return set_error(SPMV_ERR_ARG, "null argument");
+    *out = nullptr;
+    spmv_plan *p = new (std::nothrow) spmv_plan(*src);    // scalars + host vectors
+    if (!p) return set_error(SPMV_ERR_NOMEM, "out of host memory");
+    p->bufs = new (std::nothrow) PlanBufs();
+    p->wsp_state = nullptr; p->stream = nullptr; p->ev0 = p->ev1 = nullptr;
+    const PlanBufs *sb = reinterpret_cast<const PlanBufs *>(src->bufs);
+    for (const DevBuf &b : sb->v)
+        *reinterpret_cast<void **>(reinterpret_cast<char *>(p) + b.slot) = nullptr;
+    int rc = SPMV_OK;
+    for (const DevBuf &b : sb->v) {
+        void **slot = reinterpret_cast<void **>(reinterpret_cast<char *>(p) + b.slot);
+        void *const *from = reinterpret_cast<void *const *>(reinterpret_cast<const char *>(src) + b.slot);
+        cudaError_t e = cudaMalloc(slot, b.bytes);
+        if (e == cudaSuccess) {
+            bufs(p)->v.push_back(b);
+            e = cudaMemcpy(*slot, *from, b.bytes, cudaMemcpyDeviceToDevice);
+        }
+        if (e != cudaSuccess) { rc = cuda_error(e, "clone: cudaMalloc/cudaMemcpy"); break; }
+    }
+    if (!rc && src->variant == SPMV_WSP) rc = clone_wsp_state(src, p);
+    if (!rc) {
+        cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = cuda_error(e, "clone: stream/event");
+    }
+    if (rc) { spmv_plan_destroy(p); return rc; }
+    *out = p;
+    return SPMV_OK;
+}
+
+int spmv_plan_info(const spmv_plan_t *p, spmv_plan_info_t *info)
+{
+    if (!p || !info) return set_error(SPMV_ERR_ARG, "null argument");
+    std::memset(info, 0, sizeof *info);
+    info->variant = p->variant; info->M = p->M; info->N = p->N; info->nnz = p->nnz;
+    info->device_bytes = p->device_bytes; info->scratch_bytes = p->scratch_bytes;
+    info->kernels_per_run = p->kernels_per_run;
+    info->grid_x = (int)p->grid.x; info->grid_y = (int)p->grid.y; info->block = p->block;
+    info->smem_bytes = p->smem;
+    info->index_bits = p->variant == SPMV_WSP ? p->wsp.index_bits
+                       : (p->variant == SPMV_ASP ? 0 : p->panel.index_bits);
+    info->row_splits = p->row_splits;
+    info->warps_per_col = p->wsp.warps_per_col;
+    info->slab_cols = (p->variant == SPMV_AWSP || p->variant == SPMV_TCSR) ? p->panel.slab_cols : 0;
+    return SPMV_OK;
+}
+
+int spmv_plan_traffic(const spmv_plan_t *p, const float *x, double *alg_bytes, double *phys_bytes,
+                      int64_t *nnz_touched)
+{
+    if (!p) return set_error(SPMV_ERR_ARG, "null plan");
+    if (!x && p->M > 0 && p->variant != SPMV_WSP) return set_error(SPMV_ERR_ARG, "x is null");
+    const double M = (double)p->M, N = (double)p->N;
+    const double vec = 4.0 * M + 4.0 * N;
+    const double split_io = p->row_splits > 1 ? 2.0 * 4.0 * p->row_splits * (double)p->col_tiles * p->tile_width : 0.0;
+    double alg = 0, phys = 0;
+    int64_t touched = 0;
+    if (p->variant == SPMV_WSP) {
+        touched = p->nnz;
+        alg = 8.0 * touched + 4.0 * (N + 1) + vec;
+        phys = (double)p->fmt_groups * (16.0 + 4.0 * p->wsp.index_bits / 8.0) + 4.0 * (N + 1) + vec;
+    } else if (p->variant == SPMV_ASP) {
+        int64_t mnz = 0;
+        for (int64_t j = 0; j < p->M; j++) mnz += (x[j] != 0.0f);
+        touched = mnz * p->N;
+        alg = 4.0 * mnz * N + vec;
+        phys = alg + split_io;
+    } else {
+        int64_t groups = 0;
+        for (int64_t j = 0; j < p->M; j++)
+            if (x[j] != 0.0f) { touched += p->row_nnz[j]; groups += p->row_groups[j]; }
+        alg = 8.0 * touched + 4.0 * (N + 1) + vec;
+        phys = (double)groups * (16.0 + 4.0 * p->panel.index_bits / 8.0) + (double)p->off_bytes + vec + split_io;
+    }
+    if (alg_bytes) *alg_bytes = alg;
+    if (phys_bytes) *phys_bytes = phys;
+    if (nnz_touched) *nnz_touched = touched;
+    return SPMV_OK;
+}
+
+int spmv_run(spmv_plan_t *p, const float *d_x, float *d_y, void *stream)
+{
+    if (!p) return set_error(SPMV_ERR_ARG, "null plan");
+    if ((!d_x && p->M > 0) || (!d_y && p->N > 0)) return set_error(SPMV_ERR_ARG, "null device vector");
+    if ((reinterpret_cast<uintptr_t>(d_y) & 15) != 0) return set_error(SPMV_ERR_ARG, "d_y must be 16-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (p->variant) {
+    case SPMV_WSP: return launch_wsp(p, d_x, d_y, st);
+    case SPMV_ASP: return launch_asp(p, d_x, d_y, st);
+    case SPMV_AWSP:
+    case SPMV_TCSR: return launch_panel(p, d_x, d_y, st);
+    }
+    return set_error(SPMV_ERR_ARG, "corrupt plan");
+}
+
+int spmv_run_host(spmv_plan_t *p, const float *x, float *y, float *timing_ms)
+{
+    if (!p) return set_error(SPMV_ERR_ARG, "null plan");
+    if ((!x && p->M > 0) || (!y && p->N > 0)) return set_error(SPMV_ERR_ARG, "null host vector");
+    if (p->M > 0) SPMV_CUDA(cudaMemcpyAsync(p->d_x, x, (size_t)p->M * 4, cudaMemcpyHostToDevice, p->stream));
+    if (timing_ms) SPMV_CUDA(cudaEventRecord(p->ev0, p->stream));
+    int rc = spmv_run(p, p->d_x, p->d_y, p->stream);
+    if (rc) return rc;
+    if (timing_ms) SPMV_CUDA(cudaEventRecord(p->ev1, p->stream));
+    if (p->N > 0) SPMV_CUDA(cudaMemcpyAsync(y, p->d_y, (size_t)p->N * 4, cudaMemcpyDeviceToHost, p->stream));
+    SPMV_CUDA(cudaStreamSynchronize(p->stream));
+    if (timing_ms) SPMV_CUDA(cudaEventElapsedTime(timing_ms, p->ev0, p->ev1));
+    return SPMV_OK;
+}
+
+int spmv_compact_x(const float *d_x, int64_t M, int32_t *d_idx, float *d_val, int32_t *d_count,
+                   void *d_scratch, size_t scratch_bytes, void *stream)
+{
+    if (!d_count || (M > 0 && (!d_x || !d_idx || !d_val))) return set_error(SPMV_ERR_ARG, "null argument");
+    return launch_compact(d_x, M, d_idx, d_val, d_count, d_scratch, scratch_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t spmv_compact_x_scratch_bytes(int64_t M) { return compact_scratch_bytes(M); }
+
+int spmv_partition_columns(int64_t N, int parts, int64_t align, const int64_t *col_ptr, int64_t *bounds)
+{
+    if (!bounds || parts <= 0 || N < 0) return set_error(SPMV_ERR_ARG, "bad partition request");
+    if (align <= 0) align = 32;
+    if (align % 32) return set_error(SPMV_ERR_ARG, "align must be a multiple of 32");
+    const int64_t units = (N + align - 1) / align;          // slabs of `align` columns
+    bounds[0] = 0;
+    if (!col_ptr) {
+        for (int g = 1; g <= parts; g++) bounds[g] = std::min(N, ((units * g) / parts) * align);
+    } else {
+        const int64_t total = col_ptr[N] - col_ptr[0];
+        int64_t u = 0;
+        for (int g = 1; g < parts; g++) {
+            // smallest slab boundary whose prefix reaches g/parts of the non-zeros
+            const double want = (double)total * g / parts;
+            while (u < units && (double)(col_ptr[std::min(N, u * align)] - col_ptr[0]) < want) u++;
+            bounds[g] = std::max(bounds[g - 1], std::min(N, u * align));
+        }
+    }
+    bounds[parts] = N;
+    return SPMV_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,64 @@
+// formats.hpp — host descriptions of the device formats (see DESIGN.md "Data layout in HBM").
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace spmv {
+
+// ------------------------------------------------------------------------------------------
+// WSP: CSR of A^T ("one list per output column", the orientation of the reference's
+// CSRMatrix, matrix_csr.cpp:8-22) cut into 128-bit groups of four non-zeros:
+//   vals  float4 [groups]            values, list order = ascending row
+//   idx   ushort4|uint4 [groups]     row index of each value (16 bit when M < 65536)
+//   colptr uint32 [N+1]              first group of each column (sentinel included)
+// A column is padded to a multiple of 4 with (value 0, index M); the kernels keep one zero
+// at x[M] so a pad contributes an exact 0 regardless of x.
+// ------------------------------------------------------------------------------------------
+struct HostWsp {
+    int64_t M = 0, N = 0, nnz = 0, groups = 0;
+    int index_bits = 16;
+    std::vector<uint32_t> colptr;  // N+1
+    std::vector<float> vals;       // 4*groups
+    std::vector<uint16_t> idx16;   // 4*groups (index_bits == 16)
+    std::vector<uint32_t> idx32;   // 4*groups (index_bits == 32)
+    int64_t max_col_groups = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+// Row-panel format shared by AWSP and TCSR.  A is cut into column slabs of `slab_cols`
+// outputs (a power of two, 256 .. 4096).  The unit of storage is the *row segment* (one row
+// of one slab): its non-zeros in ascending column order, cut into 128-bit groups of four:
+//   vals  float4 [groups]                     values
+//   idx   uchar4 (slab_cols == 256) | ushort4 column of each value inside the slab
+// A segment is padded to a multiple of 4 with (value 0, column 0); the kernels skip
+// value == 0 entries (stored values are never zero), so a pad never touches an accumulator.
+// Segments are laid out slab-major, row-minor, so everything one (slab, row-range) CTA reads
+// is one contiguous run, and the segment of a row with x[row] == 0 is simply not read.
+//   AWSP: off[slab*(M+1) + row]  = first group of the segment (32-bit, row-addressable)
+//   TCSR: 32 consecutive rows form a tile (the reference's tcsr.cpp tiles are 32x32):
+//         tile_off[slab*(RB+1) + rb] = first group of the tile (32-bit)
+//         rel[(slab*RB + rb)*32 + r] = first group of row r inside the tile (16-bit)
+//         i.e. a two-level offset: 2 bytes per segment instead of 4.
+// ------------------------------------------------------------------------------------------
+constexpr int kTileRows = 32;
+constexpr int kMinSlabCols = 256;
+constexpr int kMaxSlabCols = 4096;
+
+struct HostPanel {
+    int64_t M = 0, N = 0, nnz = 0, groups = 0;
+    int slab_cols = 256;
+    int index_bits = 8;          // 8 when slab_cols == 256, else 16
+    int slabs = 0;
+    int row_blocks = 0;          // ceil(M/32)
+    bool tiled = false;          // false: AWSP (per-row offsets), true: TCSR (two-level offsets)
+    std::vector<uint32_t> off;       // AWSP: slabs*(M+1);  TCSR: slabs*(row_blocks+1)
+    std::vector<uint16_t> rel;       // TCSR: slabs*row_blocks*32
+    std::vector<float> vals;         // 4*groups
+    std::vector<uint8_t> idx8;       // 4*groups (index_bits == 8)
+    std::vector<uint16_t> idx16;     // 4*groups (index_bits == 16)
+    std::vector<int32_t> row_nnz;    // [M]  stored nnz per row (all slabs)   — traffic accounting
+    std::vector<int32_t> row_groups; // [M]  groups per row (all slabs)       — traffic accounting
+    std::vector<int32_t> row_segs;   // [M]  non-empty segments per row       — traffic accounting
+};
+
+} // namespace spmv

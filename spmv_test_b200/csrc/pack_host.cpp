@@ -1,0 +1,452 @@
+// pack_host.cpp — host packers.
+//   (1) this library's device formats (formats.hpp) from a dense matrix or from CSR(A^T);
+//   (2) the reference's six host layouts, bit-exact, behind spmv_ref_pack() — what the drop-in
+//       format classes (host/formats.cpp) are made of.
+// Written from the layout descriptions in SURVEY.md §2a; checked bit-for-bit against the
+// reference packers through the oracle (tests/test_ref_layouts.py).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "formats.hpp"
+#include "plan.hpp"
+#include "spmv_b200.h"
+
+namespace spmv {
+
+// ---------------------------------------------------------------------------- WSP ---------
+static void wsp_finish_layout(HostWsp &w, const std::vector<int64_t> &col_nnz)
+{
+    const int64_t N = w.N;
+    w.colptr.resize(N + 1);
+    int64_t g = 0, mx = 0;
+    for (int64_t i = 0; i < N; i++) {
+        w.colptr[i] = (uint32_t)g;
+        int64_t cg = (col_nnz[i] + 3) / 4;
+        mx = std::max(mx, cg);
+        g += cg;
+    }
+    w.colptr[N] = (uint32_t)g;
+    w.groups = g;
+    w.max_col_groups = mx;
+    w.vals.assign((size_t)g * 4, 0.0f);
+    if (w.index_bits == 16) w.idx16.assign((size_t)g * 4, (uint16_t)w.M);
+    else w.idx32.assign((size_t)g * 4, (uint32_t)w.M);
+}
+
+int pack_wsp_dense(int64_t M, int64_t N, const float *A, int64_t lda, int index_bits, HostWsp &w)
+{
+    w.M = M; w.N = N;
+    w.index_bits = index_bits ? index_bits : (M < 65536 ? 16 : 32);
+    if (w.index_bits == 16 && M >= 65536) return SPMV_ERR_ARG;
+    std::vector<int64_t> cnt((size_t)N, 0);
+    for (int64_t j = 0; j < M; j++) {            // row-major sweep: rows arrive in ascending order
+        const float *row = A + j * lda;
+        for (int64_t i = 0; i < N; i++) cnt[i] += (row[i] != 0.0f);
+    }
+    int64_t nnz = 0;
+    for (int64_t i = 0; i < N; i++) nnz += cnt[i];
+    w.nnz = nnz;
+    if ((nnz + 3 * N) / 4 >= (int64_t)UINT32_MAX) return SPMV_ERR_UNSUPPORTED;
+    wsp_finish_layout(w, cnt);
+    std::vector<int64_t> cur((size_t)N);
+    for (int64_t i = 0; i < N; i++) cur[i] = (int64_t)w.colptr[i] * 4;
+    for (int64_t j = 0; j < M; j++) {
+        const float *row = A + j * lda;
+        for (int64_t i = 0; i < N; i++) {
+            float v = row[i];
+            if (v != 0.0f) {
+                int64_t p = cur[i]++;
+                w.vals[p] = v;
+                if (w.index_bits == 16) w.idx16[p] = (uint16_t)j; else w.idx32[p] = (uint32_t)j;
+            }
+        }
+    }
+    return SPMV_OK;
+}
+
+int pack_wsp_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx,
+                 const float *values, int index_bits, HostWsp &w)
+{
+    w.M = M; w.N = N;
+    w.index_bits = index_bits ? index_bits : (M < 65536 ? 16 : 32);
+    if (w.index_bits == 16 && M >= 65536) return SPMV_ERR_ARG;
+    std::vector<int64_t> cnt((size_t)N, 0);
+    int64_t nnz = 0;
+    for (int64_t i = 0; i < N; i++) {
+        int64_t c = 0;
+        for (int64_t k = col_ptr[i]; k < col_ptr[i + 1]; k++) {
+            if (row_idx[k] < 0 || row_idx[k] >= M) return SPMV_ERR_ARG;
+            c += (values[k] != 0.0f);
+        }
+        cnt[i] = c; nnz += c;
+    }
+    w.nnz = nnz;
+    if ((nnz + 3 * N) / 4 >= (int64_t)UINT32_MAX) return SPMV_ERR_UNSUPPORTED;
+    wsp_finish_layout(w, cnt);
+    for (int64_t i = 0; i < N; i++) {
+        int64_t p = (int64_t)w.colptr[i] * 4;
+        for (int64_t k = col_ptr[i]; k < col_ptr[i + 1]; k++) {
+            if (values[k] == 0.0f) continue;
+            w.vals[p] = values[k];
+            if (w.index_bits == 16) w.idx16[p] = (uint16_t)row_idx[k]; else w.idx32[p] = (uint32_t)row_idx[k];
+            p++;
+        }
+    }
+    return SPMV_OK;
+}
+
+// ---------------------------------------------------------------------------- panel -------
+namespace {
+
+// Row source abstraction: yields the non-zeros of (slab, row) in ascending column order.
+struct DenseSource {
+    const float *A; int64_t lda, N; int W;
+    void begin_slab(int) {}
+    int get(int slab, int64_t row, uint16_t *cols, float *vals) const
+    {
+        const int64_t c0 = (int64_t)slab * W;
+        const int cw = (int)std::min<int64_t>(W, N - c0);
+        const float *p = A + row * lda + c0;
+        int n = 0;
+        for (int c = 0; c < cw; c++) {
+            const float v = p[c];
+            if (v != 0.0f) { cols[n] = (uint16_t)c; vals[n] = v; n++; }
+        }
+        return n;
+    }
+};
+
+struct CscSource {
+    const int64_t *col_ptr; const int32_t *row_idx; const float *values; int64_t M, N; int W;
+    // per-slab row buckets
+    std::vector<int64_t> start;    // M+1
+    std::vector<uint16_t> col;     // local column of each entry, row-bucketed
+    std::vector<float> val;
+    void begin_slab(int slab)
+    {
+        const int64_t c0 = (int64_t)slab * W;
+        const int cw = (int)std::min<int64_t>(W, N - c0);
+        start.assign((size_t)M + 1, 0);
+        for (int c = 0; c < cw; c++)
+            for (int64_t k = col_ptr[c0 + c]; k < col_ptr[c0 + c + 1]; k++)
+                if (values[k] != 0.0f) start[(size_t)row_idx[k] + 1]++;
+        for (int64_t r = 0; r < M; r++) start[r + 1] += start[r];
+        col.resize((size_t)start[M]); val.resize((size_t)start[M]);
+        std::vector<int64_t> cur(start.begin(), start.end() - 1);
+        for (int c = 0; c < cw; c++)      // ascending columns => column order inside each row
+            for (int64_t k = col_ptr[c0 + c]; k < col_ptr[c0 + c + 1]; k++)
+                if (values[k] != 0.0f) {
+                    const int64_t p = cur[row_idx[k]]++;
+                    col[p] = (uint16_t)c; val[p] = values[k];
+                }
+    }
+    int get(int, int64_t row, uint16_t *cols, float *vals) const
+    {
+        const int64_t b = start[row], e = start[row + 1];
+        for (int64_t p = b; p < e; p++) { cols[p - b] = col[p]; vals[p - b] = val[p]; }
+        return (int)(e - b);
+    }
+};
+
+template <class Source>
+int pack_panel(int64_t M, int64_t N, bool tiled, int W, Source &src, HostPanel &P)
+{
+    if (W < kMinSlabCols || W > kMaxSlabCols || (W & (W - 1))) return SPMV_ERR_ARG;
+    P.M = M; P.N = N; P.tiled = tiled;
+    P.slab_cols = W;
+    P.index_bits = (W == 256) ? 8 : 16;
+    P.slabs = (int)((N + W - 1) / W);
+    P.row_blocks = (int)((M + kTileRows - 1) / kTileRows);
+    P.row_nnz.assign((size_t)M, 0);
+    P.row_groups.assign((size_t)M, 0);
+    P.row_segs.assign((size_t)M, 0);
+    P.nnz = 0; P.groups = 0;
+    P.vals.clear(); P.idx8.clear(); P.idx16.clear(); P.rel.clear();
+    const int64_t per_slab = tiled ? (P.row_blocks + 1) : (M + 1);
+    P.off.assign((size_t)P.slabs * per_slab, 0);
+    if (tiled) P.rel.assign((size_t)P.slabs * P.row_blocks * kTileRows, 0);
+    std::vector<uint16_t> cols((size_t)W);
+    std::vector<float> vals((size_t)W);
+
+    auto emit = [&](int n) {
+        const int g = (n + 3) / 4;
+        const size_t at = P.vals.size();
+        P.vals.resize(at + (size_t)g * 4, 0.0f);
+        std::memcpy(&P.vals[at], vals.data(), sizeof(float) * (size_t)n);
+        if (P.index_bits == 8) {
+            P.idx8.resize(at + (size_t)g * 4, 0);
+            for (int k = 0; k < n; k++) P.idx8[at + k] = (uint8_t)cols[k];
+        } else {
+            P.idx16.resize(at + (size_t)g * 4, 0);
+            std::memcpy(&P.idx16[at], cols.data(), sizeof(uint16_t) * (size_t)n);
+        }
+        P.groups += g;
+        return g;
+    };
+
+    for (int s = 0; s < P.slabs; s++) {
+        src.begin_slab(s);
+        for (int rb = 0; rb < P.row_blocks; rb++) {
+            const int64_t tile_first = P.groups;
+            if (tiled) P.off[(size_t)s * per_slab + rb] = (uint32_t)tile_first;
+            for (int r = 0; r < kTileRows; r++) {
+                const int64_t row = (int64_t)rb * kTileRows + r;
+                if (tiled) P.rel[((size_t)s * P.row_blocks + rb) * kTileRows + r] = (uint16_t)(P.groups - tile_first);
+                if (row >= M) continue;
+                if (!tiled) P.off[(size_t)s * per_slab + row] = (uint32_t)P.groups;
+                const int n = src.get(s, row, cols.data(), vals.data());
+                if (n) {
+                    const int g = emit(n);
+                    P.row_nnz[row] += n; P.row_groups[row] += g; P.row_segs[row] += 1; P.nnz += n;
+                }
+            }
+            if (P.groups - tile_first > 65535) return SPMV_ERR_UNSUPPORTED;   // u16 rel offsets
+            if (P.groups >= (int64_t)UINT32_MAX) return SPMV_ERR_UNSUPPORTED;
+        }
+        P.off[(size_t)s * per_slab + (tiled ? P.row_blocks : M)] = (uint32_t)P.groups;
+    }
+    return SPMV_OK;
+}
+} // namespace
+
+// Slab width from the density: aim at ~100 non-zeros per row segment so the 128-bit group
+// padding, the per-segment offsets and the DRAM sector fringe stay a few percent; 8-bit
+// columns (slab 256) whenever the density allows it.
+int choose_slab_cols(int64_t M, int64_t N, int64_t nnz)
+{
+    if (M <= 0 || N <= 0 || nnz <= 0) return kMinSlabCols;
+    const double density = (double)nnz / ((double)M * (double)N);
+    if (density >= 0.125) return 256;
+    int w = 512;
+    while (w < kMaxSlabCols && w * density < 100.0) w <<= 1;
+    return w;
+}
+
+int pack_panel_dense(int64_t M, int64_t N, const float *A, int64_t lda, bool tiled, int slab_cols,
+                     HostPanel &P)
+{
+    if (slab_cols <= 0) {
+        int64_t nnz = 0;
+        for (int64_t j = 0; j < M; j++) {
+            const float *row = A + j * lda;
+            for (int64_t i = 0; i < N; i++) nnz += (row[i] != 0.0f);
+        }
+        slab_cols = choose_slab_cols(M, N, nnz);
+    }
+    DenseSource src{A, lda, N, slab_cols};
+    return pack_panel(M, N, tiled, slab_cols, src, P);
+}
+
+int pack_panel_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx,
+                   const float *values, bool tiled, int slab_cols, HostPanel &P)
+{
+    int64_t nnz = 0;
+    for (int64_t k = col_ptr[0]; k < col_ptr[N]; k++) {
+        if (row_idx[k] < 0 || row_idx[k] >= M) return SPMV_ERR_ARG;
+        nnz += (values[k] != 0.0f);
+    }
+    if (slab_cols <= 0) slab_cols = choose_slab_cols(M, N, nnz);
+    CscSource src{col_ptr, row_idx, values, M, N, slab_cols, {}, {}, {}};
+    return pack_panel(M, N, tiled, slab_cols, src, P);
+}
+
+} // namespace spmv
+
+// ==========================================================================================
+// Reference host layouts (C-ABI, CPU only)
+// ==========================================================================================
+namespace {
+
+template <class T> T *take(std::vector<T> &v, int64_t &n)
+{
+    n = (int64_t)v.size();
+    T *p = (T *)std::malloc(std::max<size_t>(v.size(), 1) * sizeof(T));
+    if (p && !v.empty()) std::memcpy(p, v.data(), v.size() * sizeof(T));
+    return p;
+}
+
+inline void set_bit(std::vector<uint32_t> &bm, size_t bit) { bm[bit >> 5] |= 1u << (bit & 31); }
+
+// matrix_csr.cpp:5-23 — one (value,row) list per output column, row_pointers WITHOUT sentinel.
+void ref_csr(int M, int N, const float *A, spmv_ref_packed_t *o)
+{
+    std::vector<int32_t> ptr((size_t)N), idx;
+    std::vector<float> val;
+    std::vector<int32_t> cnt((size_t)N, 0);
+    for (int j = 0; j < M; j++)
+        for (int i = 0; i < N; i++) cnt[i] += (A[(size_t)j * N + i] != 0.0f);
+    int32_t run = 0;
+    for (int i = 0; i < N; i++) { ptr[i] = run; run += cnt[i]; }
+    idx.resize((size_t)run); val.resize((size_t)run);
+    std::vector<int32_t> cur(ptr);
+    for (int j = 0; j < M; j++)
+        for (int i = 0; i < N; i++) {
+            float v = A[(size_t)j * N + i];
+            if (v != 0.0f) { int32_t p = cur[i]++; idx[p] = j; val[p] = v; }
+        }
+    o->i32_a = take(ptr, o->n_i32_a);
+    o->i32_b = take(idx, o->n_i32_b);
+    o->f32 = take(val, o->n_f32);
+}
+
+// tcsr.cpp:5-38 — tiles slab-major; inside a tile word = column, bit = row; blk_idx with sentinel.
+void ref_tcsr(int M, int N, const float *A, spmv_ref_packed_t *o)
+{
+    const int TR = M / 32, TC = N / 32;
+    std::vector<uint32_t> bm((size_t)M * N / 32, 0u);
+    std::vector<int32_t> blk((size_t)TR * TC + 1, 0);
+    std::vector<float> val;
+    size_t tile = 0;
+    for (int tc = 0; tc < TC; tc++)
+        for (int tr = 0; tr < TR; tr++, tile++) {
+            for (int c = 0; c < 32; c++) {
+                uint32_t word = 0;
+                for (int r = 0; r < 32; r++) {
+                    float v = A[(size_t)(tr * 32 + r) * N + tc * 32 + c];
+                    if (v != 0.0f) { word |= 1u << r; val.push_back(v); }
+                }
+                bm[tile * 32 + c] = word;
+            }
+            blk[tile + 1] = (int32_t)val.size();
+        }
+    o->i32_a = take(blk, o->n_i32_a);
+    o->u32 = take(bm, o->n_u32);
+    o->f32 = take(val, o->n_f32);
+}
+
+// wsp.cpp:3-40 — column-major bit order (bit i*M+j), ELL-padded values (nz_max_m per column).
+void ref_wsp(int M, int N, const float *A, spmv_ref_packed_t *o)
+{
+    std::vector<uint32_t> bm((size_t)M * N / 32, 0u);
+    std::vector<int32_t> cnt((size_t)N, 0);
+    for (int j = 0; j < M; j++)
+        for (int i = 0; i < N; i++)
+            if (A[(size_t)j * N + i] != 0.0f) { cnt[i]++; set_bit(bm, (size_t)i * M + j); }
+    int nzmax = 0;
+    for (int i = 0; i < N; i++) nzmax = std::max(nzmax, cnt[i]);
+    std::vector<float> val((size_t)N * nzmax, 0.0f);
+    std::fill(cnt.begin(), cnt.end(), 0);
+    for (int j = 0; j < M; j++)
+        for (int i = 0; i < N; i++) {
+            float v = A[(size_t)j * N + i];
+            if (v != 0.0f) val[(size_t)i * nzmax + cnt[i]++] = v;
+        }
+    o->u32 = take(bm, o->n_u32);
+    o->f32 = take(val, o->n_f32);
+    o->aux[0] = nzmax; o->aux[1] = N;
+}
+
+// asp.cpp:3-14 — dense, 32x32 tiles slab-major, row-major inside the tile.
+void ref_asp(int M, int N, const float *A, spmv_ref_packed_t *o)
+{
+    std::vector<float> val((size_t)M * N);
+    const int TR = M / 32;
+    for (int j = 0; j < M; j++)
+        for (int i = 0; i < N; i++) {
+            size_t tile = (size_t)(i / 32) * TR + j / 32;
+            val[tile * 1024 + (size_t)(j % 32) * 32 + i % 32] = A[(size_t)j * N + i];
+        }
+    o->f32 = take(val, o->n_f32);
+}
+
+// awsp.cpp:3-49 — tiles slab-major; word = row, bit = column; each tile padded to nz_bk_max.
+void ref_awsp(int M, int N, const float *A, spmv_ref_packed_t *o)
+{
+    const int TR = M / 32, TC = N / 32;
+    std::vector<uint32_t> bm((size_t)M * N / 32, 0u);
+    std::vector<int32_t> tcnt((size_t)TR * TC, 0);
+    for (int j = 0; j < M; j++)
+        for (int i = 0; i < N; i++)
+            if (A[(size_t)j * N + i] != 0.0f) {
+                size_t tile = (size_t)(i / 32) * TR + j / 32;
+                tcnt[tile]++;
+                bm[tile * 32 + j % 32] |= 1u << (i % 32);
+            }
+    int bkmax = 0;
+    for (int32_t c : tcnt) bkmax = std::max(bkmax, c);
+    std::vector<float> val((size_t)TR * TC * bkmax, 0.0f);
+    std::fill(tcnt.begin(), tcnt.end(), 0);
+    for (int j = 0; j < M; j++)       // row-major sweep = row-major order inside every tile
+        for (int i = 0; i < N; i++) {
+            float v = A[(size_t)j * N + i];
+            if (v != 0.0f) {
+                size_t tile = (size_t)(i / 32) * TR + j / 32;
+                val[tile * bkmax + tcnt[tile]++] = v;
+            }
+        }
+    o->u32 = take(bm, o->n_u32);
+    o->f32 = take(val, o->n_f32);
+    o->aux[0] = bkmax;
+}
+
+// awsp_ref.cpp:4-58 — bitmap word slab*M+row, bit = column; values per (slab, quarter of M),
+// quarter q padded to its max over slabs; warp_nz_offset = inclusive prefix of the maxima.
+void ref_awsp_ref(int M, int N, const float *A, spmv_ref_packed_t *o)
+{
+    const int TC = N / 32, Q = M / 4;
+    std::vector<uint32_t> bm((size_t)M * N / 32, 0u);
+    std::vector<int32_t> qcnt((size_t)TC * 4, 0);
+    for (int j = 0; j < M; j++)
+        for (int i = 0; i < N; i++)
+            if (A[(size_t)j * N + i] != 0.0f) {
+                qcnt[(size_t)(i / 32) * 4 + j / Q]++;
+                bm[(size_t)(i / 32) * M + j] |= 1u << (i % 32);
+            }
+    std::vector<int32_t> off(4, 0);
+    int run = 0;
+    for (int q = 0; q < 4; q++) {
+        int mx = 0;
+        for (int s = 0; s < TC; s++) mx = std::max(mx, qcnt[(size_t)s * 4 + q]);
+        run += mx; off[q] = run;
+    }
+    const int stride = off[3];
+    std::vector<float> val((size_t)TC * stride, 0.0f);
+    std::fill(qcnt.begin(), qcnt.end(), 0);
+    for (int j = 0; j < M; j++)
+        for (int i = 0; i < N; i++) {
+            float v = A[(size_t)j * N + i];
+            if (v != 0.0f) {
+                int s = i / 32, q = j / Q;
+                int base = q ? off[q - 1] : 0;
+                val[(size_t)s * stride + base + qcnt[(size_t)s * 4 + q]++] = v;
+            }
+        }
+    o->i32_a = take(off, o->n_i32_a);
+    o->u32 = take(bm, o->n_u32);
+    o->f32 = take(val, o->n_f32);
+}
+} // namespace
+
+extern "C" int spmv_ref_pack(int layout, int M, int N, const float *A, spmv_ref_packed_t *out)
+{
+    if (!out || (!A && (int64_t)M * N > 0)) return spmv::set_error(SPMV_ERR_ARG, "spmv_ref_pack: null argument");
+    std::memset(out, 0, sizeof *out);
+    if (M < 0 || N < 0 || M % 32 || N % 32)
+        return spmv::set_error(SPMV_ERR_SHAPE, "spmv_ref_pack: M and N must be multiples of 32 (tester.cpp:9-10)");
+    if ((int64_t)M * N >= ((int64_t)1 << 31))
+        return spmv::set_error(SPMV_ERR_SHAPE, "spmv_ref_pack: M*N overflows the reference's int indexing");
+    try {
+        switch (layout) {
+        case SPMV_LAYOUT_CSR: ref_csr(M, N, A, out); break;
+        case SPMV_LAYOUT_TCSR: ref_tcsr(M, N, A, out); break;
+        case SPMV_LAYOUT_WSP: ref_wsp(M, N, A, out); break;
+        case SPMV_LAYOUT_ASP: ref_asp(M, N, A, out); break;
+        case SPMV_LAYOUT_AWSP: ref_awsp(M, N, A, out); break;
+        case SPMV_LAYOUT_AWSP_REF: ref_awsp_ref(M, N, A, out); break;
+        default: return spmv::set_error(SPMV_ERR_ARG, "spmv_ref_pack: unknown layout");
+        }
+    } catch (const std::bad_alloc &) {
+        spmv_ref_packed_free(out);
+        return spmv::set_error(SPMV_ERR_NOMEM, "spmv_ref_pack: out of host memory");
+    }
+    return SPMV_OK;
+}
+
+extern "C" void spmv_ref_packed_free(spmv_ref_packed_t *p)
+{
+    if (!p) return;
+    std::free(p->i32_a); std::free(p->i32_b); std::free(p->u32); std::free(p->f32);
+    std::memset(p, 0, sizeof *p);
+}

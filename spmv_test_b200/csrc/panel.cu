@@ -1,0 +1,238 @@
+// panel.cu — activation+weight-sparse SGEMV on the row-panel format (formats.hpp: HostPanel).
+//
+// Replaces awsp_kernel_v0/v1/v2 (reference awsp.cu:5-317), awsp_ref_kernel (awsp_ref.cu:6-185)
+// and csr_tiling_kernel (csr_tiling.cu:24-114).  The reference gives every 32-column slab to
+// one CTA, walks a per-row bitmap (word -> popc -> address -> one 4-byte load per lane) and
+// uses x only as a load predicate: every bitmap word and every x is still read.  Here
+//   * a CTA owns (column slab, row range); each of its warps walks whole 32-row blocks;
+//   * lane l of a warp looks at row l of the block: x[row] and the segment's group range.
+//     ballot(x != 0 && segment non-empty) is the activation compaction: rows with x == 0 are
+//     never visited, so their values/indices are never read from HBM;
+//   * a visited segment is streamed as 128-bit groups (float4 values + 4 packed column ids),
+//     32 groups per warp instruction, kDepth chunks in flight per warp (register ring);
+//   * products are accumulated into a per-warp fp32 accumulator row in shared memory
+//     (columns inside one segment are distinct, segments are consumed in ascending row order,
+//     warps never share an accumulator) — no atomics, fixed summation order;
+//   * warps are summed in warp order, row splits in split order (integer ticket picks the CTA
+//     that does the final sum; the order of the sum itself is fixed).
+// AWSP addresses segments through a 32-bit per-row table, TCSR through 32-bit per-tile plus
+// 16-bit in-tile offsets (the reference's blk_idx, tcsr.cpp:13,34, made two-level).
+#include <algorithm>
+
+#include "common.cuh"
+#include "plan.hpp"
+
+namespace spmv {
+
+namespace {
+
+constexpr int kPanelWarps = 8;
+constexpr int kPanelThreads = kPanelWarps * 32;
+constexpr int kDepth = 4;
+
+template <int IDXB> struct ColIdx;
+template <> struct ColIdx<8> {
+    using Vec = uint32_t;
+    static __device__ __forceinline__ Vec load(const void *base, uint32_t g)
+    {
+        Vec r;
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(reinterpret_cast<const Vec *>(base) + g));
+        return r;
+    }
+    static __device__ __forceinline__ void unpack(Vec v, uint32_t (&c)[4])
+    {
+        c[0] = v & 0xffu; c[1] = (v >> 8) & 0xffu; c[2] = (v >> 16) & 0xffu; c[3] = v >> 24;
+    }
+    static __device__ __forceinline__ Vec zero() { return 0u; }
+};
+template <> struct ColIdx<16> {
+    using Vec = uint2;
+    static __device__ __forceinline__ Vec load(const void *base, uint32_t g)
+    {
+        return ldg_stream_u2(reinterpret_cast<const Vec *>(base) + g);
+    }
+    static __device__ __forceinline__ void unpack(Vec v, uint32_t (&c)[4])
+    {
+        c[0] = v.x & 0xffffu; c[1] = v.x >> 16; c[2] = v.y & 0xffffu; c[3] = v.y >> 16;
+    }
+    static __device__ __forceinline__ Vec zero() { return make_uint2(0u, 0u); }
+};
+
+template <int IDXB, bool TILED>
+__global__ void __launch_bounds__(kPanelThreads)
+panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
+             const uint32_t *__restrict__ off, const uint16_t *__restrict__ rel,
+             const float *__restrict__ x, float *__restrict__ y, float *__restrict__ partial,
+             unsigned *__restrict__ tickets, int M, int N, int W, int row_blocks,
+             int blocks_per_split, int splits)
+{
+    extern __shared__ __align__(16) float acc_all[];      // [kPanelWarps][W]
+    __shared__ int last_flag;
+    using CI = ColIdx<IDXB>;
+    using IVec = typename CI::Vec;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slab = blockIdx.x, split = blockIdx.y;
+    float *acc = acc_all + (size_t)warp * W;
+    for (int c = lane; c < W; c += 32) acc[c] = 0.0f;
+    __syncwarp();
+
+    const int rb_end = min(row_blocks, (split + 1) * blocks_per_split);
+    int rb_next = split * blocks_per_split + warp;        // block whose metadata is in n*
+
+    // ---- metadata of one 32-row block: lane = row ------------------------------------------
+    float nxv = 0.f; uint32_t ng0 = 0, ng1 = 0;
+    auto load_meta = [&](int rb) {
+        const int row = rb * 32 + lane;
+        nxv = row < M ? __ldg(x + row) : 0.0f;
+        if (TILED) {
+            const size_t t = (size_t)slab * (row_blocks + 1) + rb;
+            const uint32_t tb = __ldg(off + t), te = __ldg(off + t + 1);
+            const uint32_t r = __ldg(rel + ((size_t)slab * row_blocks + rb) * 32 + lane);
+            const uint32_t rn = __shfl_down_sync(kFull, r, 1);
+            ng0 = tb + r;
+            ng1 = lane < 31 ? tb + rn : te;
+        } else {
+            const size_t o = (size_t)slab * ((size_t)M + 1) + row;
+            ng0 = row < M ? __ldg(off + o) : 0u;
+            ng1 = row < M ? __ldg(off + o + 1) : 0u;
+        }
+    };
+    if (rb_next < rb_end) load_meta(rb_next);
+
+    // ---- flat iterator over (block, active row, chunk of 32 groups) ---------------------------
+    float bxv = 0.f; uint32_t bg0 = 0, bg1 = 0;           // current block's per-lane metadata
+    unsigned mask = 0;                                    // active rows of it not yet visited
+    uint32_t g = 0, gend = 0; float xv = 0.f;             // current chunk (warp-uniform)
+    bool live = true;
+    auto next_row = [&]() {
+        while (mask == 0) {
+            if (rb_next >= rb_end) { live = false; return; }
+            bxv = nxv; bg0 = ng0; bg1 = ng1;
+            mask = __ballot_sync(kFull, bxv != 0.0f && bg1 > bg0);
+            rb_next += kPanelWarps;
+            if (rb_next < rb_end) load_meta(rb_next);
+        }
+        const int i = __ffs(mask) - 1;
+        mask &= mask - 1;
+        g = __shfl_sync(kFull, bg0, i);
+        gend = __shfl_sync(kFull, bg1, i);
+        xv = __shfl_sync(kFull, bxv, i);
+    };
+    next_row();
+
+    // ---- kDepth chunks in flight -----------------------------------------------------------------
+    float4 v[kDepth]; IVec ix[kDepth]; float px[kDepth]; bool lv[kDepth];
+    auto issue = [&](int d) {
+        lv[d] = live;
+        if (!live) return;
+        const uint32_t gg = g + lane;
+        if (gg < gend) { v[d] = ldg_stream_f4(vals + gg); ix[d] = CI::load(idx, gg); }
+        else { v[d] = make_float4(0.f, 0.f, 0.f, 0.f); ix[d] = CI::zero(); }
+        px[d] = xv;
+        g += 32;
+        if (g >= gend) next_row();
+    };
+    auto consume = [&](int d) {
+        uint32_t c[4];
+        CI::unpack(ix[d], c);
+        const float4 a = v[d];
+        const float p = px[d];
+        // columns inside a segment are distinct: read all four, then write back the live ones
+        float r0 = acc[c[0]], r1 = acc[c[1]], r2 = acc[c[2]], r3 = acc[c[3]];
+        r0 = fmaf(a.x, p, r0); r1 = fmaf(a.y, p, r1); r2 = fmaf(a.z, p, r2); r3 = fmaf(a.w, p, r3);
+        if (a.x != 0.0f) acc[c[0]] = r0;
+        if (a.y != 0.0f) acc[c[1]] = r1;
+        if (a.z != 0.0f) acc[c[2]] = r2;
+        if (a.w != 0.0f) acc[c[3]] = r3;
+        __syncwarp();                                     // next chunk may be another row
+    };
+#pragma unroll
+    for (int d = 0; d < kDepth; d++) issue(d);
+    while (lv[0]) {
+#pragma unroll
+        for (int d = 0; d < kDepth; d++) {
+            if (lv[d]) consume(d);
+            issue(d);
+        }
+    }
+
+    // ---- fixed-order sum over warps, then over row splits ----------------------------------------
+    __syncthreads();
+    const int col0 = slab * W;
+    const int n_valid = min(W, N - col0);
+    const size_t npad = (size_t)gridDim.x * W;
+    for (int c = tid; c < n_valid; c += kPanelThreads) {
+        float s = acc_all[c];
+#pragma unroll
+        for (int w = 1; w < kPanelWarps; w++) s += acc_all[(size_t)w * W + c];
+        if (splits == 1) y[col0 + c] = s;
+        else partial[(size_t)split * npad + col0 + c] = s;
+    }
+    if (splits > 1)
+        split_reduce_finish(y, partial, tickets, slab, splits, W, n_valid, npad, &last_flag);
+}
+
+template <int IDXB, bool TILED>
+int launch_variant(spmv_plan *p, const float *x, float *y, cudaStream_t st)
+{
+    auto k = panel_kernel<IDXB, TILED>;
+    if (p->smem > 48 * 1024)
+        SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem));
+    const DevPanel &d = p->panel;
+    k<<<p->grid, kPanelThreads, p->smem, st>>>(reinterpret_cast<const float4 *>(d.vals), d.idx, d.off, d.rel, x, y,
+                                              p->partial, p->tickets, (int)p->M, (int)p->N, d.slab_cols,
+                                              d.row_blocks, d.blocks_per_split, p->row_splits);
+    SPMV_CUDA(cudaGetLastError());
+    return SPMV_OK;
+}
+
+} // namespace
+
+int launch_panel(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st)
+{
+    if (p->N == 0) return SPMV_OK;
+    const DevPanel &d = p->panel;
+    if (d.index_bits == 8) return d.tiled ? launch_variant<8, true>(p, d_x, d_y, st) : launch_variant<8, false>(p, d_x, d_y, st);
+    return d.tiled ? launch_variant<16, true>(p, d_x, d_y, st) : launch_variant<16, false>(p, d_x, d_y, st);
+}
+
+// Geometry: grid = (slabs, row splits).  A warp should own at least two 32-row blocks (so
+// the metadata prefetch has something to overlap), the grid should cover the SMs about
+// twice, and a CTA should stream clearly more than it spends zeroing / summing its
+// accumulator rows (kPanelWarps * slab_cols floats).
+int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o)
+{
+    DevPanel &d = p->panel;
+    d.slab_cols = h.slab_cols; d.index_bits = h.index_bits; d.slabs = h.slabs;
+    d.row_blocks = h.row_blocks; d.tiled = h.tiled; d.warps = kPanelWarps;
+    p->block = kPanelThreads;
+    p->smem = kPanelWarps * h.slab_cols * (int)sizeof(float);
+    p->tile_width = h.slab_cols;
+    p->col_tiles = h.slabs;
+    p->kernels_per_run = 1;
+
+    const int rb = std::max(1, h.row_blocks);
+    const int resident = std::max(1, std::min(8, (p->max_smem_optin > 0 ? p->max_smem_optin : 227 * 1024) / (p->smem + 1024)));
+    const int slabs = std::max(1, h.slabs);
+    int splits;
+    if (o && o->row_splits > 0) {
+        splits = std::min(o->row_splits, rb);
+    } else {
+        splits = (rb + 2 * kPanelWarps - 1) / (2 * kPanelWarps);          // two blocks per warp
+        if ((int64_t)splits * slabs < 2 * p->sm_count) splits = (rb + kPanelWarps - 1) / kPanelWarps;
+        // wide slabs: keep the accumulator overhead small against the streamed bytes
+        const int cap = std::max(1, (2 * p->sm_count * resident) / slabs);
+        splits = std::min(splits, cap);
+        splits = std::max(1, std::min(splits, rb));
+    }
+    d.blocks_per_split = (rb + splits - 1) / splits;
+    splits = (rb + d.blocks_per_split - 1) / d.blocks_per_split;      // no empty splits
+    p->row_splits = splits;
+    p->grid = dim3((unsigned)slabs, (unsigned)splits, 1);
+    if (p->smem > (p->max_smem_optin > 0 ? p->max_smem_optin : 227 * 1024))
+        return set_error(SPMV_ERR_UNSUPPORTED, "panel: %d bytes of shared memory exceed the device limit", p->smem);
+    return alloc_split_scratch(p);
+}
+
+} // namespace spmv

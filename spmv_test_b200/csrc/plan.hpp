@@ -1,0 +1,120 @@
+// plan.hpp — the opaque spmv_plan and the internal interfaces between capi.cu, the packers
+// and the kernel launchers.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "formats.hpp"
+#include "spmv_b200.h"
+
+namespace spmv {
+
+int set_error(int code, const char *fmt, ...);   // stores the thread's message, returns code
+int cuda_error(cudaError_t e, const char *what); // SPMV_ERR_CUDA + message (never exits)
+
+#define SPMV_CUDA(call)                                                        \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) return ::spmv::cuda_error(e_, #call);           \
+    } while (0)
+
+// host packers (pack_host.cpp)
+int pack_wsp_dense(int64_t M, int64_t N, const float *A, int64_t lda, int index_bits, HostWsp &w);
+int pack_wsp_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx,
+                 const float *values, int index_bits, HostWsp &w);
+int pack_panel_dense(int64_t M, int64_t N, const float *A, int64_t lda, bool tiled, int slab_cols,
+                     HostPanel &P);
+int pack_panel_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx,
+                   const float *values, bool tiled, int slab_cols, HostPanel &P);
+int choose_slab_cols(int64_t M, int64_t N, int64_t nnz);
+
+struct DevWsp {
+    uint32_t *colptr = nullptr;
+    float *vals = nullptr;
+    void *idx = nullptr;
+    int index_bits = 16;
+    int warps_per_col = 1;
+    bool x_in_smem = true;
+};
+
+struct DevAsp {
+    float *A = nullptr;     // dense row-major, leading dimension ld (multiple of 4)
+    int64_t ld = 0;
+    int tile_cols = 0;      // columns per CTA
+    int rows_per_split = 0;
+};
+
+struct DevPanel {
+    uint32_t *off = nullptr;
+    uint16_t *rel = nullptr;
+    float *vals = nullptr;
+    void *idx = nullptr;
+    int slab_cols = 256;
+    int index_bits = 8;
+    int slabs = 0, row_blocks = 0;
+    int warps = 8;
+    int blocks_per_split = 0;   // row blocks (of 32 rows) per CTA
+    bool tiled = false;
+};
+
+} // namespace spmv
+
+struct spmv_plan {
+    int variant = 0;
+    int device = 0;
+    int64_t M = 0, N = 0, nnz = 0;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+
+    spmv::DevWsp wsp;
+    void *bufs = nullptr;       // spmv::PlanBufs (capi.cu): registry of device allocations
+    void *wsp_state = nullptr;  // spmv::WspState (wsp.cu): the length bins
+    int wsp_team = 0;
+    spmv::DevAsp asp;
+    spmv::DevPanel panel;
+
+    // split-reduction scratch (asp/awsp/tcsr)
+    int row_splits = 1;
+    int col_tiles = 0;          // number of output tiles (tickets)
+    int tile_width = 0;
+    float *partial = nullptr;   // [row_splits][col_tiles*tile_width]
+    unsigned *tickets = nullptr;
+
+    // launch geometry of the main kernel
+    dim3 grid{1, 1, 1};
+    int block = 0;
+    int smem = 0;
+    int kernels_per_run = 1;
+
+    // host-side accounting
+    int64_t device_bytes = 0, scratch_bytes = 0;
+    std::vector<int32_t> row_nnz;    // awsp/tcsr: stored nnz per row
+    std::vector<int32_t> row_groups; //            groups per row
+    std::vector<int32_t> row_segs;   //            non-empty segments per row
+    int64_t fmt_groups = 0;          // wsp / panel: total groups
+    int64_t off_bytes = 0;           // bytes of the offset tables
+
+    // staging buffers for spmv_run_host
+    float *d_x = nullptr, *d_y = nullptr;
+    cudaStream_t stream = nullptr;  // owned, used by spmv_run_host
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace spmv {
+// kernel launchers (one per .cu); all are asynchronous on `st`
+int launch_wsp(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st);
+int launch_asp(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st);
+int launch_panel(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st);
+int launch_compact(const float *d_x, int64_t M, int32_t *d_idx, float *d_val, int32_t *d_count,
+                   void *d_scratch, size_t scratch_bytes, cudaStream_t st);
+size_t compact_scratch_bytes(int64_t M);
+// geometry setup (fills grid/block/smem, allocates scratch)
+int configure_wsp(spmv_plan *p, const HostWsp &w, const spmv_options_t *o);
+int configure_asp(spmv_plan *p, const spmv_options_t *o);
+int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o);
+void destroy_wsp_state(spmv_plan *p);
+int clone_wsp_state(const spmv_plan *src, spmv_plan *dst);
+int alloc_split_scratch(spmv_plan *p);   // partial + tickets from row_splits/col_tiles/tile_width
+} // namespace spmv

@@ -1,0 +1,303 @@
+// wsp.cu — weight-sparse SGEMV on the CSR(A^T) "V4" streams (formats.hpp: HostWsp).
+//
+// Replaces wsp_kernel_v0/v1 (reference wsp.cu:4-138) and csr_naive_kernel
+// (csr_naive.cu:6-23).  The reference assigns one warp per output column and walks a column
+// bitmap: bitmap word -> popc -> address -> one 4-byte load per lane, a dependent chain with
+// one load in flight per lane.  Here every output column is a contiguous, 16-byte aligned
+// run of (float4 values, 4 x row index) groups, so a team of T threads streams it with
+// 128-bit coalesced loads, several per thread in flight, gathers x from shared memory
+// (staged once per CTA by a 1-D bulk async copy), and reduces with a fixed shuffle tree.
+// T is chosen per length bin (row-length binning), so a power-law matrix (BASELINE config 4)
+// gives 4-thread teams to its short rows and whole CTAs to its long ones.
+//
+// Determinism: lane partials (4 chains, fixed association) -> xor-shuffle tree -> fixed-order
+// cross-warp sum.  No atomics.
+#include <algorithm>
+#include <climits>
+#include <vector>
+
+#include "common.cuh"
+#include "plan.hpp"
+
+namespace spmv {
+
+namespace {
+
+constexpr int kWspBlock = 256;
+constexpr int kWspUnroll = 4;
+
+template <typename IdxVec> struct IdxTraits;
+template <> struct IdxTraits<uint2> {   // 4 x u16
+    static __device__ __forceinline__ uint2 load(const uint2 *p) { return ldg_stream_u2(p); }
+    static __device__ __forceinline__ void unpack(const uint2 &v, uint32_t (&i)[4])
+    {
+        i[0] = v.x & 0xffffu; i[1] = v.x >> 16; i[2] = v.y & 0xffffu; i[3] = v.y >> 16;
+    }
+    static __device__ __forceinline__ uint2 pad(uint32_t M) { uint32_t w = M | (M << 16); return make_uint2(w, w); }
+};
+template <> struct IdxTraits<uint4> {   // 4 x u32
+    static __device__ __forceinline__ uint4 load(const uint4 *p) { return ldg_stream_u4(p); }
+    static __device__ __forceinline__ void unpack(const uint4 &v, uint32_t (&i)[4])
+    {
+        i[0] = v.x; i[1] = v.y; i[2] = v.z; i[3] = v.w;
+    }
+    static __device__ __forceinline__ uint4 pad(uint32_t M) { return make_uint4(M, M, M, M); }
+};
+
+// T threads cooperate on one output column.  XS: x lives in shared memory.
+template <typename IdxVec, int T, bool XS>
+__global__ void __launch_bounds__(kWspBlock)
+wsp_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
+           const uint32_t *__restrict__ colptr, const int32_t *__restrict__ cols, int ncols,
+           const float *__restrict__ x, float *__restrict__ y, uint32_t M, int x_bulk_ok)
+{
+    extern __shared__ __align__(16) float xs[];          // M + 1 (+pad) floats when XS
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ float red[kWspBlock / 32];
+
+    const int tid = threadIdx.x;
+    if (XS) {
+        const uint32_t m4 = M & ~3u;                      // bulk part: whole 16-byte units
+        if (x_bulk_ok && m4) {
+            if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t done = 0;
+                mbar_expect_tx(&bar, m4 * 4u);
+                while (done < m4 * 4u) {                  // <= 32 KB per bulk copy
+                    uint32_t n = min(m4 * 4u - done, 32768u);
+                    bulk_g2s(reinterpret_cast<char *>(xs) + done, reinterpret_cast<const char *>(x) + done, n, &bar);
+                    done += n;
+                }
+            }
+            for (uint32_t j = m4 + tid; j < M; j += kWspBlock) xs[j] = x[j];
+        } else {
+            for (uint32_t j = tid; j < M; j += kWspBlock) xs[j] = x[j];
+        }
+        if (tid < 4) xs[M + tid] = 0.0f;                  // the pad slot (and alignment slack)
+    }
+
+    constexpr int kTeams = kWspBlock / T;
+    const int team_local = tid / T;
+    const int tl = tid % T;
+    const int lane = tid & 31;
+    const int team = blockIdx.x * kTeams + team_local;
+    const int nteams = gridDim.x * kTeams;
+
+    // Issue the first column's loads before waiting for x: the A stream does not depend on it.
+    if (XS) {
+        if (x_bulk_ok && (M & ~3u)) mbar_wait(&bar, 0);
+        __syncthreads();
+    }
+
+    for (int k = team; k < ncols; k += nteams) {
+        const int c = cols ? cols[k] : k;
+        const uint32_t g0 = colptr[c], g1 = colptr[c + 1];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (uint32_t g = g0 + tl; g < g1; g += T * kWspUnroll) {
+            float4 v[kWspUnroll];
+            IdxVec iv[kWspUnroll];
+#pragma unroll
+            for (int u = 0; u < kWspUnroll; u++) {
+                const uint32_t gg = g + u * T;
+                if (gg < g1) { v[u] = ldg_stream_f4(vals + gg); iv[u] = IdxTraits<IdxVec>::load(idx + gg); }
+                else { v[u] = make_float4(0.f, 0.f, 0.f, 0.f); iv[u] = IdxTraits<IdxVec>::pad(XS ? M : 0u); }
+            }
+#pragma unroll
+            for (int u = 0; u < kWspUnroll; u++) {
+                uint32_t i[4];
+                IdxTraits<IdxVec>::unpack(iv[u], i);
+                float x0, x1, x2, x3;
+                if (XS) { x0 = xs[i[0]]; x1 = xs[i[1]]; x2 = xs[i[2]]; x3 = xs[i[3]]; }
+                else {
+                    x0 = i[0] < M ? __ldg(x + i[0]) : 0.f; x1 = i[1] < M ? __ldg(x + i[1]) : 0.f;
+                    x2 = i[2] < M ? __ldg(x + i[2]) : 0.f; x3 = i[3] < M ? __ldg(x + i[3]) : 0.f;
+                }
+                a0 = fmaf(v[u].x, x0, a0); a1 = fmaf(v[u].y, x1, a1);
+                a2 = fmaf(v[u].z, x2, a2); a3 = fmaf(v[u].w, x3, a3);
+            }
+        }
+        float acc = (a0 + a1) + (a2 + a3);
+        if (T >= 32) {
+            acc = warp_sum(acc);
+            if (T == 32) {
+                if (lane == 0) y[c] = acc;
+            } else {
+                constexpr int W = T / 32;                 // warps per team
+                const int wt = (tid / 32) % (W > 0 ? W : 1);
+                const int bar_id = 1 + team_local;        // named barrier per team (0 = __syncthreads)
+                if (lane == 0) red[tid / 32] = acc;
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(T) : "memory");
+                if (wt == 0 && lane == 0) {
+                    float s = 0.f;
+                    for (int w = 0; w < W; w++) s += red[team_local * W + w];
+                    y[c] = s;
+                }
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(T) : "memory");
+            }
+        } else {
+#pragma unroll
+            for (int s = T / 2; s >= 1; s >>= 1) acc += __shfl_xor_sync(kFull, acc, s);
+            if (tl == 0) y[c] = acc;
+        }
+    }
+}
+
+struct Bin { int T; std::vector<int32_t> cols; };
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct WspBinDev { int T; int32_t *cols; int ncols; int grid; };
+
+struct WspState {            // hangs off the plan through plan->wsp_state
+    std::vector<WspBinDev> bins;
+};
+
+template <typename IdxVec, int T, bool XS>
+static int launch_one(const spmv_plan *p, const WspBinDev &b, const float *x, float *y, cudaStream_t st,
+                      size_t smem, int x_bulk_ok)
+{
+    auto k = wsp_kernel<IdxVec, T, XS>;
+    if (smem > 48 * 1024) SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<b.grid, kWspBlock, smem, st>>>(reinterpret_cast<const float4 *>(p->wsp.vals),
+                                       reinterpret_cast<const IdxVec *>(p->wsp.idx), p->wsp.colptr, b.cols,
+                                       b.ncols, x, y, (uint32_t)p->M, x_bulk_ok);
+    SPMV_CUDA(cudaGetLastError());
+    return SPMV_OK;
+}
+
+template <typename IdxVec, bool XS>
+static int launch_T(const spmv_plan *p, const WspBinDev &b, const float *x, float *y, cudaStream_t st,
+                    size_t smem, int ok)
+{
+    switch (b.T) {
+    case 4: return launch_one<IdxVec, 4, XS>(p, b, x, y, st, smem, ok);
+    case 8: return launch_one<IdxVec, 8, XS>(p, b, x, y, st, smem, ok);
+    case 16: return launch_one<IdxVec, 16, XS>(p, b, x, y, st, smem, ok);
+    case 32: return launch_one<IdxVec, 32, XS>(p, b, x, y, st, smem, ok);
+    case 64: return launch_one<IdxVec, 64, XS>(p, b, x, y, st, smem, ok);
+    case 128: return launch_one<IdxVec, 128, XS>(p, b, x, y, st, smem, ok);
+    case 256: return launch_one<IdxVec, 256, XS>(p, b, x, y, st, smem, ok);
+    }
+    return set_error(SPMV_ERR_ARG, "wsp: bad team size %d", b.T);
+}
+
+int launch_wsp(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st)
+{
+    if (p->N == 0) return SPMV_OK;
+    const WspState *s = reinterpret_cast<const WspState *>(p->wsp_state);
+    const int ok = ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) ? 1 : 0;
+    for (const WspBinDev &b : s->bins) {
+        int rc;
+        const size_t smem = p->wsp.x_in_smem ? (size_t)p->smem : 0;
+        if (p->wsp.index_bits == 16)
+            rc = p->wsp.x_in_smem ? launch_T<uint2, true>(p, b, d_x, d_y, st, smem, ok)
+                                  : launch_T<uint2, false>(p, b, d_x, d_y, st, smem, ok);
+        else
+            rc = p->wsp.x_in_smem ? launch_T<uint4, true>(p, b, d_x, d_y, st, smem, ok)
+                                  : launch_T<uint4, false>(p, b, d_x, d_y, st, smem, ok);
+        if (rc) return rc;
+    }
+    return SPMV_OK;
+}
+
+static int pow2_ceil(int64_t v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+int configure_wsp(spmv_plan *p, const HostWsp &w, const spmv_options_t *o)
+{
+    WspState *s = new WspState();
+    p->wsp_state = s;
+    p->wsp.index_bits = w.index_bits;
+    // x in shared memory when it (plus the pad slot) fits comfortably next to several CTAs/SM
+    const size_t xbytes = ((size_t)w.M + 4) * sizeof(float);
+    p->wsp.x_in_smem = xbytes <= 96 * 1024 && w.index_bits == 16;
+    if (w.index_bits == 32 && xbytes <= 96 * 1024) p->wsp.x_in_smem = true;
+    p->smem = p->wsp.x_in_smem ? (int)((xbytes + 15) & ~(size_t)15) : 0;
+    p->block = kWspBlock;
+
+    // ---- row-length binning --------------------------------------------------------------
+    // target ~8 groups (32 non-zeros) per thread; bins are powers of two in [4, 256].
+    const int64_t N = w.N;
+    auto team_for = [&](int64_t groups) {
+        int t = pow2_ceil((groups + 7) / 8);
+        return std::min(256, std::max(4, t));
+    };
+    int64_t gmin = INT64_MAX, gmax = 0;
+    for (int64_t i = 0; i < N; i++) {
+        int64_t g = (int64_t)w.colptr[i + 1] - w.colptr[i];
+        gmin = std::min(gmin, g); gmax = std::max(gmax, g);
+    }
+    const int64_t gmean = N ? (w.groups + N - 1) / N : 0;
+    int forced = 0;
+    if (o && o->warps_per_col > 0) forced = std::min(256, 32 * pow2_ceil(o->warps_per_col));
+    std::vector<Bin> bins;
+    if (forced || N == 0 || team_for(gmax) <= 2 * team_for(std::max<int64_t>(gmin, 1))) {
+        bins.push_back({forced ? forced : team_for(gmean), {}});           // one bin: all columns, no list
+    } else {
+        const int Ts[7] = {4, 8, 16, 32, 64, 128, 256};
+        for (int t : Ts) bins.push_back({t, {}});
+        for (int64_t i = 0; i < N; i++) {
+            int t = team_for((int64_t)w.colptr[i + 1] - w.colptr[i]);
+            for (Bin &b : bins) if (b.T == t) b.cols.push_back((int32_t)i);
+        }
+        std::vector<Bin> keep;
+        for (Bin &b : bins) if (!b.cols.empty()) keep.push_back(std::move(b));
+        bins.swap(keep);
+    }
+    // occupancy-sized persistent grids
+    const int ctas_per_sm = p->wsp.x_in_smem ? std::max(1, std::min(8, (int)((200 * 1024) / std::max(p->smem, 1)))) : 8;
+    for (Bin &b : bins) {
+        WspBinDev d{};
+        d.T = b.T;
+        d.ncols = b.cols.empty() ? (int)N : (int)b.cols.size();
+        d.cols = nullptr;
+        if (!b.cols.empty()) {
+            SPMV_CUDA(cudaMalloc(&d.cols, b.cols.size() * sizeof(int32_t)));
+            SPMV_CUDA(cudaMemcpy(d.cols, b.cols.data(), b.cols.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            p->device_bytes += (int64_t)b.cols.size() * 4;
+        }
+        const int teams_per_cta = kWspBlock / b.T;
+        const int64_t need = ((int64_t)d.ncols + teams_per_cta - 1) / teams_per_cta;
+        d.grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)p->sm_count * ctas_per_sm));
+        s->bins.push_back(d);
+    }
+    p->kernels_per_run = (int)s->bins.size();
+    p->grid = dim3(s->bins.empty() ? 1 : s->bins[0].grid, 1, 1);
+    p->wsp.warps_per_col = s->bins.empty() ? 0 : std::max(1, s->bins[0].T / 32);
+    p->wsp_team = s->bins.empty() ? 0 : s->bins[0].T;
+    return SPMV_OK;
+}
+
+int clone_wsp_state(const spmv_plan *src, spmv_plan *dst)
+{
+    const WspState *s = reinterpret_cast<const WspState *>(src->wsp_state);
+    WspState *d = new WspState();
+    dst->wsp_state = d;
+    if (!s) return SPMV_OK;
+    for (const WspBinDev &b : s->bins) {
+        WspBinDev nb = b;
+        nb.cols = nullptr;
+        if (b.cols) {
+            SPMV_CUDA(cudaMalloc(&nb.cols, (size_t)b.ncols * sizeof(int32_t)));
+            d->bins.push_back(nb);
+            SPMV_CUDA(cudaMemcpy(nb.cols, b.cols, (size_t)b.ncols * sizeof(int32_t), cudaMemcpyDeviceToDevice));
+        } else {
+            d->bins.push_back(nb);
+        }
+    }
+    return SPMV_OK;
+}
+
+void destroy_wsp_state(spmv_plan *p)
+{
+    WspState *s = reinterpret_cast<WspState *>(p->wsp_state);
+    if (!s) return;
+    for (WspBinDev &b : s->bins) if (b.cols) cudaFree(b.cols);
+    delete s;
+    p->wsp_state = nullptr;
+}
+
+} // namespace spmv

@@ -1,0 +1,170 @@
+"""Plan objects over the C-ABI (include/spmv_b200.h).
+
+A plan is the pack-once / run-many form of one reference launcher
+(`*_gemv_gpu(M, N, A_host, X_host, Y_host[, version])`, reference src/include/kernel.hpp:8-17,
+which re-packs and re-uploads A on every call).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+
+import numpy as np
+
+from ._cabi import LAYOUTS, VARIANTS, Options, PlanInfo, RefPacked, check, lib
+
+
+def _opts(**kw):
+    if not kw:
+        return None
+    o = Options()
+    o.struct_size = C.sizeof(Options)
+    for k, v in kw.items():
+        if v is not None:
+            setattr(o, k, int(v))
+    return C.byref(o)
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None and a.size else C.c_void_p(0)
+
+
+class Plan:
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+
+    # ---- construction ----------------------------------------------------------------------
+    @classmethod
+    def from_dense(cls, variant, A, **opts):
+        """A: 2-D float32 array, row-major; a column slab view `A[:, a:b]` of a C-contiguous
+        matrix is accepted as is (leading dimension = the parent's row length)."""
+        A = np.asarray(A)
+        if A.dtype != np.float32 or A.ndim != 2:
+            raise TypeError("A must be a 2-D float32 array")
+        M, N = A.shape
+        if A.size and (A.strides[1] != 4 or A.strides[0] % 4 or A.strides[0] < 4 * N):
+            A = np.ascontiguousarray(A)
+        lda = A.strides[0] // 4 if A.size and M > 1 else max(N, 1)
+        if lda < N:
+            lda = N
+        h = C.c_void_p()
+        check(lib().spmv_plan_create_dense(VARIANTS[variant], M, N, _ptr(A), lda, _opts(**opts), C.byref(h)))
+        p = cls(h.value)
+        p._keep = None
+        return p
+
+    @classmethod
+    def from_csc(cls, variant, M, N, col_ptr, row_idx, values, **opts):
+        """CSR(A^T) input: per output column i the entries (row, value), rows ascending —
+        the orientation of the reference's CSRMatrix (matrix_csr.cpp:8-22), 64-bit pointers
+        with the N+1 sentinel."""
+        col_ptr = np.ascontiguousarray(col_ptr, np.int64)
+        row_idx = np.ascontiguousarray(row_idx, np.int32)
+        values = np.ascontiguousarray(values, np.float32)
+        if col_ptr.size != N + 1:
+            raise ValueError("col_ptr needs N+1 entries")
+        h = C.c_void_p()
+        check(lib().spmv_plan_create_csc(VARIANTS[variant], M, N, _ptr(col_ptr), _ptr(row_idx), _ptr(values),
+                                         _opts(**opts), C.byref(h)))
+        return cls(h.value)
+
+    def clone(self):
+        h = C.c_void_p()
+        check(lib().spmv_plan_clone(self._h, C.byref(h)))
+        return Plan(h.value)
+
+    def close(self):
+        if self._h:
+            lib().spmv_plan_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- queries ---------------------------------------------------------------------------
+    def info(self):
+        i = PlanInfo()
+        check(lib().spmv_plan_info(self._h, C.byref(i)))
+        return {k: getattr(i, k) for k, _ in PlanInfo._fields_ if k != "reserved"}
+
+    def traffic(self, x):
+        """(algorithmic bytes, physical bytes, non-zeros touched) of one call with this x."""
+        x = np.ascontiguousarray(x, np.float32)
+        a, p, n = C.c_double(), C.c_double(), C.c_int64()
+        check(lib().spmv_plan_traffic(self._h, _ptr(x), C.byref(a), C.byref(p), C.byref(n)))
+        return a.value, p.value, n.value
+
+    # ---- execution -------------------------------------------------------------------------
+    def run(self, d_x, d_y, stream=None):
+        """Asynchronous y = x·A on device tensors (torch CUDA tensors or raw pointers)."""
+        px = d_x if isinstance(d_x, int) else d_x.data_ptr()
+        py = d_y if isinstance(d_y, int) else d_y.data_ptr()
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        check(lib().spmv_run(self._h, C.c_void_p(px), C.c_void_p(py), C.c_void_p(stream)))
+
+    def run_host(self, x, y=None, timing=False):
+        """Host-buffer call (H2D x, kernels, D2H y, synchronise) — the per-call part of a
+        reference launcher.  Returns y (and the kernels' device milliseconds if timing)."""
+        info = self.info()
+        x = np.ascontiguousarray(x, np.float32)
+        if x.size != info["M"]:
+            raise ValueError("x has the wrong length")
+        if y is None:
+            y = np.empty(info["N"], np.float32)
+        ms = C.c_float(-1.0)
+        check(lib().spmv_run_host(self._h, _ptr(x), _ptr(y), C.byref(ms) if timing else None))
+        return (y, ms.value) if timing else y
+
+    def run_host_ptr(self, x_ptr, y_ptr):
+        """Same with raw host pointers (pinned buffers owned by the caller)."""
+        check(lib().spmv_run_host(self._h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), None))
+
+
+def compact_x(d_x, stream=None):
+    """Device activation compaction: returns (idx int32[count], val float32[count]) tensors."""
+    import torch
+    M = d_x.numel()
+    idx = torch.empty(max(M, 1), dtype=torch.int32, device=d_x.device)
+    val = torch.empty(max(M, 1), dtype=torch.float32, device=d_x.device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=d_x.device)
+    nb = lib().spmv_compact_x_scratch_bytes(M)
+    scratch = torch.empty(max(nb, 4), dtype=torch.uint8, device=d_x.device)
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    check(lib().spmv_compact_x(C.c_void_p(d_x.data_ptr()), M, C.c_void_p(idx.data_ptr()), C.c_void_p(val.data_ptr()),
+                               C.c_void_p(cnt.data_ptr()), C.c_void_p(scratch.data_ptr()), nb, C.c_void_p(stream)))
+    n = int(cnt.item())
+    return idx[:n], val[:n]
+
+
+def ref_pack(layout, A):
+    """The reference's host layouts (bit-exact re-implementation, CPU only): what the drop-in
+    CSRMatrix / TCSRMatrix / WSPMatrix / ASPMatrix / AWSPMatrix / AWSPRefMatrix classes hold."""
+    A = np.ascontiguousarray(A, np.float32)
+    M, N = A.shape
+    s = RefPacked()
+    check(lib().spmv_ref_pack(LAYOUTS[layout], M, N, _ptr(A), C.byref(s)))
+
+    def grab(p, n, dt):
+        if not p:
+            return None
+        if n == 0:
+            return np.zeros(0, dt)
+        return np.ctypeslib.as_array(p, shape=(n,)).astype(dt, copy=True)
+
+    out = SimpleNamespace(i32_a=grab(s.i32_a, s.n_i32_a, np.int32), i32_b=grab(s.i32_b, s.n_i32_b, np.int32),
+                          u32=grab(s.u32, s.n_u32, np.uint32), f32=grab(s.f32, s.n_f32, np.float32),
+                          aux=list(s.aux))
+    lib().spmv_ref_packed_free(C.byref(s))
+    return out
