@@ -182,6 +182,31 @@ SPMV_API size_t spmv_compact_x_scratch_bytes(int64_t M);
 SPMV_API int spmv_partition_columns(int64_t N, int parts, int64_t align, const int64_t *col_ptr,
                            int64_t *bounds /* parts+1 */);
 
+/* ---- device-format inspection (host only; no GPU needed) ---------------------------------- */
+/*
+ * Packs like spmv_plan_create_dense / _csc would, but hands the host image of the device
+ * format back instead of uploading it: the CPU test-suite decodes it to check the packers
+ * (group padding, offsets, column ids) without a GPU.  Not a compute path.
+ *   SPMV_WSP        vals[4*groups], idx (u16|u32)[4*groups], off = colptr[N+1]
+ *   SPMV_AWSP       vals, idx (u8|u16)[4*groups], off[slabs*(M+1)]
+ *   SPMV_TCSR       vals, idx, off = tile_off[slabs*(row_blocks+1)], rel[slabs*row_blocks*32]
+ */
+typedef struct spmv_packed_dump {
+    int32_t  variant, index_bits, slab_cols, slabs, row_blocks, reserved;
+    int64_t  M, N, nnz, groups;
+    float    *vals;  int64_t n_vals;
+    void     *idx;   int64_t idx_bytes;
+    uint32_t *off;   int64_t n_off;
+    uint16_t *rel;   int64_t n_rel;
+} spmv_packed_dump_t;
+
+SPMV_API int  spmv_pack_dump_dense(int variant, int64_t M, int64_t N, const float *A, int64_t lda,
+                                   const spmv_options_t *opts, spmv_packed_dump_t *out);
+SPMV_API int  spmv_pack_dump_csc(int variant, int64_t M, int64_t N, const int64_t *col_ptr,
+                                 const int32_t *row_idx, const float *values,
+                                 const spmv_options_t *opts, spmv_packed_dump_t *out);
+SPMV_API void spmv_pack_dump_free(spmv_packed_dump_t *d);
+
 /* ---- reference host layouts (CPU only; used by the drop-in format classes) ----------------- */
 /*
  * Bit-exact re-implementations of the reference's six host packers.  No GPU needed.

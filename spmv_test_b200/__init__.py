@@ -7,5 +7,5 @@ for tests and bench.py, and the column-slab partitioner used for the multi-GPU c
 no CPU compute path: every call that produces y needs the CUDA library and a GPU.
 """
 from ._cabi import LIB_PATH, SpmvError, lib, VARIANTS, LAYOUTS  # noqa: F401
-from .plan import Plan, compact_x, ref_pack  # noqa: F401
+from .plan import Plan, compact_x, pack_dump, ref_pack  # noqa: F401
 from .partition import column_bounds, ShardedSgemv  # noqa: F401

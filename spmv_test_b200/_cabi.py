@@ -16,7 +16,7 @@ SYMBOLS = [
     "spmv_plan_create_csc", "spmv_plan_info", "spmv_plan_destroy", "spmv_plan_clone",
     "spmv_plan_traffic", "spmv_run", "spmv_run_host", "spmv_compact_x",
     "spmv_compact_x_scratch_bytes", "spmv_partition_columns", "spmv_ref_pack",
-    "spmv_ref_packed_free",
+    "spmv_ref_packed_free", "spmv_pack_dump_dense", "spmv_pack_dump_csc", "spmv_pack_dump_free",
 ]
 
 
@@ -46,6 +46,16 @@ class RefPacked(C.Structure):
                 ("u32", C.POINTER(C.c_uint32)), ("n_u32", C.c_int64),
                 ("f32", C.POINTER(C.c_float)), ("n_f32", C.c_int64),
                 ("aux", C.c_int32 * 4)]
+
+
+class PackedDump(C.Structure):
+    _fields_ = [("variant", C.c_int32), ("index_bits", C.c_int32), ("slab_cols", C.c_int32), ("slabs", C.c_int32),
+                ("row_blocks", C.c_int32), ("reserved", C.c_int32),
+                ("M", C.c_int64), ("N", C.c_int64), ("nnz", C.c_int64), ("groups", C.c_int64),
+                ("vals", C.POINTER(C.c_float)), ("n_vals", C.c_int64),
+                ("idx", C.c_void_p), ("idx_bytes", C.c_int64),
+                ("off", C.POINTER(C.c_uint32)), ("n_off", C.c_int64),
+                ("rel", C.POINTER(C.c_uint16)), ("n_rel", C.c_int64)]
 
 
 _lib = None
@@ -80,6 +90,10 @@ def lib():
     L.spmv_ref_pack.argtypes = [i32, i32, i32, vp, C.POINTER(RefPacked)]
     L.spmv_ref_packed_free.argtypes = [C.POINTER(RefPacked)]
     L.spmv_ref_packed_free.restype = None
+    L.spmv_pack_dump_dense.argtypes = [i32, i64, i64, vp, i64, C.POINTER(Options), C.POINTER(PackedDump)]
+    L.spmv_pack_dump_csc.argtypes = [i32, i64, i64, vp, vp, vp, C.POINTER(Options), C.POINTER(PackedDump)]
+    L.spmv_pack_dump_free.argtypes = [C.POINTER(PackedDump)]
+    L.spmv_pack_dump_free.restype = None
     if L.spmv_abi_version() != 1:
         raise RuntimeError("libspmv_b200.so ABI version mismatch")
     _lib = L

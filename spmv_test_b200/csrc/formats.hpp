@@ -30,8 +30,9 @@ struct HostWsp {
 // of one slab): its non-zeros in ascending column order, cut into 128-bit groups of four:
 //   vals  float4 [groups]                     values
 //   idx   uchar4 (slab_cols == 256) | ushort4 column of each value inside the slab
-// A segment is padded to a multiple of 4 with (value 0, column 0); the kernels skip
-// value == 0 entries (stored values are never zero), so a pad never touches an accumulator.
+// A segment is padded to a multiple of 4 with (value 0, smallest column absent from the
+// segment): a pad adds an exact 0 to an accumulator no real entry of that row touches, so the
+// kernels need no per-entry predicate and no two entries of a segment share a column.
 // Segments are laid out slab-major, row-minor, so everything one (slab, row-range) CTA reads
 // is one contiguous run, and the segment of a row with x[row] == 0 is simply not read.
 //   AWSP: off[slab*(M+1) + row]  = first group of the segment (32-bit, row-addressable)

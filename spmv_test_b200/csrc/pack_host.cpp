@@ -173,13 +173,18 @@ int pack_panel(int64_t M, int64_t N, bool tiled, int W, Source &src, HostPanel &
     auto emit = [&](int n) {
         const int g = (n + 3) / 4;
         const size_t at = P.vals.size();
+        // pads carry value 0 and the smallest column that is ABSENT from the segment, so the
+        // kernel can treat them like real entries: they add an exact 0 to an accumulator no
+        // real entry of this row touches (n % 4 != 0 implies n < W, so such a column exists).
+        uint16_t absent = 0;
+        for (int k = 0; k < n && cols[k] == absent; k++) absent++;
         P.vals.resize(at + (size_t)g * 4, 0.0f);
         std::memcpy(&P.vals[at], vals.data(), sizeof(float) * (size_t)n);
         if (P.index_bits == 8) {
-            P.idx8.resize(at + (size_t)g * 4, 0);
+            P.idx8.resize(at + (size_t)g * 4, (uint8_t)absent);
             for (int k = 0; k < n; k++) P.idx8[at + k] = (uint8_t)cols[k];
         } else {
-            P.idx16.resize(at + (size_t)g * 4, 0);
+            P.idx16.resize(at + (size_t)g * 4, absent);
             std::memcpy(&P.idx16[at], cols.data(), sizeof(uint16_t) * (size_t)n);
         }
         P.groups += g;
@@ -449,4 +454,96 @@ extern "C" void spmv_ref_packed_free(spmv_ref_packed_t *p)
     if (!p) return;
     std::free(p->i32_a); std::free(p->i32_b); std::free(p->u32); std::free(p->f32);
     std::memset(p, 0, sizeof *p);
+}
+
+// ==========================================================================================
+// Device-format inspection (host only)
+// ==========================================================================================
+namespace {
+template <class T> T *dup_vec(const std::vector<T> &v)
+{
+    T *p = (T *)std::malloc(std::max<size_t>(v.size(), 1) * sizeof(T));
+    if (p && !v.empty()) std::memcpy(p, v.data(), v.size() * sizeof(T));
+    return p;
+}
+
+void dump_wsp(const spmv::HostWsp &w, spmv_packed_dump_t *o)
+{
+    o->variant = SPMV_WSP; o->index_bits = w.index_bits; o->M = w.M; o->N = w.N; o->nnz = w.nnz; o->groups = w.groups;
+    o->vals = dup_vec(w.vals); o->n_vals = (int64_t)w.vals.size();
+    if (w.index_bits == 16) { o->idx = dup_vec(w.idx16); o->idx_bytes = (int64_t)w.idx16.size() * 2; }
+    else { o->idx = dup_vec(w.idx32); o->idx_bytes = (int64_t)w.idx32.size() * 4; }
+    o->off = dup_vec(w.colptr); o->n_off = (int64_t)w.colptr.size();
+}
+
+void dump_panel(const spmv::HostPanel &h, int variant, spmv_packed_dump_t *o)
+{
+    o->variant = variant; o->index_bits = h.index_bits; o->slab_cols = h.slab_cols; o->slabs = h.slabs;
+    o->row_blocks = h.row_blocks; o->M = h.M; o->N = h.N; o->nnz = h.nnz; o->groups = h.groups;
+    o->vals = dup_vec(h.vals); o->n_vals = (int64_t)h.vals.size();
+    if (h.index_bits == 8) { o->idx = dup_vec(h.idx8); o->idx_bytes = (int64_t)h.idx8.size(); }
+    else { o->idx = dup_vec(h.idx16); o->idx_bytes = (int64_t)h.idx16.size() * 2; }
+    o->off = dup_vec(h.off); o->n_off = (int64_t)h.off.size();
+    if (h.tiled) { o->rel = dup_vec(h.rel); o->n_rel = (int64_t)h.rel.size(); }
+}
+
+int dump_common_check(int variant, int64_t M, int64_t N, spmv_packed_dump_t *out)
+{
+    if (!out) return spmv::set_error(SPMV_ERR_ARG, "null output");
+    std::memset(out, 0, sizeof *out);
+    if (variant == SPMV_ASP) return spmv::set_error(SPMV_ERR_UNSUPPORTED, "asp keeps A dense: nothing to dump");
+    if (variant < SPMV_WSP || variant > SPMV_TCSR) return spmv::set_error(SPMV_ERR_ARG, "unknown variant %d", variant);
+    if (M < 0 || N < 0 || N % 32) return spmv::set_error(SPMV_ERR_SHAPE, "bad shape %lld x %lld", (long long)M, (long long)N);
+    return SPMV_OK;
+}
+} // namespace
+
+extern "C" int spmv_pack_dump_dense(int variant, int64_t M, int64_t N, const float *A, int64_t lda,
+                                    const spmv_options_t *opts, spmv_packed_dump_t *out)
+{
+    int rc = dump_common_check(variant, M, N, out);
+    if (rc) return rc;
+    if ((!A && M * N > 0) || lda < N) return spmv::set_error(SPMV_ERR_ARG, "bad A / lda");
+    try {
+        if (variant == SPMV_WSP) {
+            spmv::HostWsp w;
+            rc = spmv::pack_wsp_dense(M, N, A, lda, opts ? opts->index_bits : 0, w);
+            if (!rc) dump_wsp(w, out);
+        } else {
+            spmv::HostPanel h;
+            rc = spmv::pack_panel_dense(M, N, A, lda, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h);
+            if (!rc) dump_panel(h, variant, out);
+        }
+    } catch (const std::bad_alloc &) { rc = SPMV_ERR_NOMEM; }
+    if (rc) return spmv::set_error(rc, "pack failed");
+    return SPMV_OK;
+}
+
+extern "C" int spmv_pack_dump_csc(int variant, int64_t M, int64_t N, const int64_t *col_ptr,
+                                  const int32_t *row_idx, const float *values,
+                                  const spmv_options_t *opts, spmv_packed_dump_t *out)
+{
+    int rc = dump_common_check(variant, M, N, out);
+    if (rc) return rc;
+    if (!col_ptr) return spmv::set_error(SPMV_ERR_ARG, "col_ptr is null");
+    try {
+        if (variant == SPMV_WSP) {
+            spmv::HostWsp w;
+            rc = spmv::pack_wsp_csc(M, N, col_ptr, row_idx, values, opts ? opts->index_bits : 0, w);
+            if (!rc) dump_wsp(w, out);
+        } else {
+            spmv::HostPanel h;
+            rc = spmv::pack_panel_csc(M, N, col_ptr, row_idx, values, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h);
+            if (!rc) dump_panel(h, variant, out);
+        }
+    } catch (const std::bad_alloc &) { rc = SPMV_ERR_NOMEM; }
+    if (rc) return spmv::set_error(rc, "pack failed");
+    return SPMV_OK;
+}
+
+extern "C" void spmv_pack_dump_free(spmv_packed_dump_t *d)
+{
+    if (!d) return;
+    std::free(d->vals); std::free(d->idx); std::free(d->off); std::free(d->rel);
+    std::memset(d, 0, sizeof *d);
 }

@@ -9,7 +9,9 @@
 //     ballot(x != 0 && segment non-empty) is the activation compaction: rows with x == 0 are
 //     never visited, so their values/indices are never read from HBM;
 //   * a visited segment is streamed as 128-bit groups (float4 values + 4 packed column ids),
-//     32 groups per warp instruction, kDepth chunks in flight per warp (register ring);
+//     32 groups per chunk, kStages chunks in flight per warp through a cp.async ring in shared
+//     memory (commit/wait groups give a true FIFO; a register ring collapses to one load in
+//     flight because its loads share scoreboard slots — measured, profiles/r01_notes.md);
 //   * products are accumulated into a per-warp fp32 accumulator row in shared memory
 //     (columns inside one segment are distinct, segments are consumed in ascending row order,
 //     warps never share an accumulator) — no atomics, fixed summation order;
@@ -28,35 +30,37 @@ namespace {
 
 constexpr int kPanelWarps = 8;
 constexpr int kPanelThreads = kPanelWarps * 32;
-constexpr int kDepth = 4;
+constexpr int kStages = 8;                   // chunks in flight per warp (cp.async groups)
 
 template <int IDXB> struct ColIdx;
 template <> struct ColIdx<8> {
-    using Vec = uint32_t;
-    static __device__ __forceinline__ Vec load(const void *base, uint32_t g)
+    using Vec = uint32_t;                    // 4 x u8
+    static __device__ __forceinline__ void copy(Vec *dst, const void *base, uint32_t g)
     {
-        Vec r;
-        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(reinterpret_cast<const Vec *>(base) + g));
-        return r;
+        cp_async4(dst, reinterpret_cast<const Vec *>(base) + g);
     }
     static __device__ __forceinline__ void unpack(Vec v, uint32_t (&c)[4])
     {
         c[0] = v & 0xffu; c[1] = (v >> 8) & 0xffu; c[2] = (v >> 16) & 0xffu; c[3] = v >> 24;
     }
-    static __device__ __forceinline__ Vec zero() { return 0u; }
 };
 template <> struct ColIdx<16> {
-    using Vec = uint2;
-    static __device__ __forceinline__ Vec load(const void *base, uint32_t g)
+    using Vec = uint2;                       // 4 x u16
+    static __device__ __forceinline__ void copy(Vec *dst, const void *base, uint32_t g)
     {
-        return ldg_stream_u2(reinterpret_cast<const Vec *>(base) + g);
+        cp_async8(dst, reinterpret_cast<const Vec *>(base) + g);
     }
     static __device__ __forceinline__ void unpack(Vec v, uint32_t (&c)[4])
     {
         c[0] = v.x & 0xffffu; c[1] = v.x >> 16; c[2] = v.y & 0xffffu; c[3] = v.y >> 16;
     }
-    static __device__ __forceinline__ Vec zero() { return make_uint2(0u, 0u); }
 };
+
+// per-warp shared memory: [acc: W floats][vals ring: kStages x 32 float4][idx ring][meta: 32 x uint4]
+template <int IDXB> __host__ __device__ constexpr int warp_smem_bytes(int W)
+{
+    return W * 4 + kStages * 32 * 16 + kStages * 32 * (IDXB == 8 ? 4 : 8) + 32 * 16;
+}
 
 template <int IDXB, bool TILED>
 __global__ void __launch_bounds__(kPanelThreads)
@@ -66,14 +70,18 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
              unsigned *__restrict__ tickets, int M, int N, int W, int row_blocks,
              int blocks_per_split, int splits)
 {
-    extern __shared__ __align__(16) float acc_all[];      // [kPanelWarps][W]
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int last_flag;
     using CI = ColIdx<IDXB>;
     using IVec = typename CI::Vec;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slab = blockIdx.x, split = blockIdx.y;
-    float *acc = acc_all + (size_t)warp * W;
+    unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes<IDXB>(W);
+    float *acc = reinterpret_cast<float *>(wbase);
+    float4 *ring_v = reinterpret_cast<float4 *>(wbase + (size_t)W * 4);
+    IVec *ring_i = reinterpret_cast<IVec *>(wbase + (size_t)W * 4 + kStages * 32 * 16);
+    uint4 *meta = reinterpret_cast<uint4 *>(wbase + (size_t)W * 4 + kStages * 32 * 16 + kStages * 32 * sizeof(IVec));
     for (int c = lane; c < W; c += 32) acc[c] = 0.0f;
     __syncwarp();
 
@@ -101,71 +109,81 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     if (rb_next < rb_end) load_meta(rb_next);
 
     // ---- flat iterator over (block, active row, chunk of 32 groups) ---------------------------
-    float bxv = 0.f; uint32_t bg0 = 0, bg1 = 0;           // current block's per-lane metadata
-    unsigned mask = 0;                                    // active rows of it not yet visited
+    // The activation compaction: ballot over x != 0 (and a non-empty segment), then an
+    // order-preserving popc scatter of (first group, end group, x) into the warp's list.
+    int n_rows = 0, ri = 0;                               // active rows of the current block
     uint32_t g = 0, gend = 0; float xv = 0.f;             // current chunk (warp-uniform)
     bool live = true;
     auto next_row = [&]() {
-        while (mask == 0) {
+        while (ri == n_rows) {
             if (rb_next >= rb_end) { live = false; return; }
-            bxv = nxv; bg0 = ng0; bg1 = ng1;
-            mask = __ballot_sync(kFull, bxv != 0.0f && bg1 > bg0);
+            const bool active = nxv != 0.0f && ng1 > ng0;
+            const unsigned mask = __ballot_sync(kFull, active);
+            __syncwarp();                                 // earlier reads of the list are done
+            if (active) meta[__popc(mask & ((1u << lane) - 1u))] = make_uint4(ng0, ng1, __float_as_uint(nxv), 0u);
+            __syncwarp();
+            n_rows = __popc(mask); ri = 0;
             rb_next += kPanelWarps;
             if (rb_next < rb_end) load_meta(rb_next);
         }
-        const int i = __ffs(mask) - 1;
-        mask &= mask - 1;
-        g = __shfl_sync(kFull, bg0, i);
-        gend = __shfl_sync(kFull, bg1, i);
-        xv = __shfl_sync(kFull, bxv, i);
+        const uint4 m = meta[ri++];
+        g = m.x; gend = m.y; xv = __uint_as_float(m.z);
     };
     next_row();
 
-    // ---- kDepth chunks in flight -----------------------------------------------------------------
-    float4 v[kDepth]; IVec ix[kDepth]; float px[kDepth]; bool lv[kDepth];
-    auto issue = [&](int d) {
-        lv[d] = live;
-        if (!live) return;
-        const uint32_t gg = g + lane;
-        if (gg < gend) { v[d] = ldg_stream_f4(vals + gg); ix[d] = CI::load(idx, gg); }
-        else { v[d] = make_float4(0.f, 0.f, 0.f, 0.f); ix[d] = CI::zero(); }
-        px[d] = xv;
-        g += 32;
-        if (g >= gend) next_row();
+    // ---- kStages chunks in flight: cp.async ring, one commit group per chunk -------------------
+    float px[kStages]; int nv[kStages];                   // x of the chunk's row, valid lanes
+    auto issue = [&](int s) {
+        nv[s] = 0;
+        if (live) {
+            const uint32_t gg = g + lane;
+            if (gg < gend) {
+                cp_async16(ring_v + s * 32 + lane, vals + gg);
+                CI::copy(ring_i + s * 32 + lane, idx, gg);
+            }
+            nv[s] = (int)min(32u, gend - g);
+            px[s] = xv;
+            g += 32;
+            if (g >= gend) next_row();
+        }
+        cp_async_commit();
     };
-    auto consume = [&](int d) {
-        uint32_t c[4];
-        CI::unpack(ix[d], c);
-        const float4 a = v[d];
-        const float p = px[d];
-        // columns inside a segment are distinct: read all four, then write back the live ones
-        float r0 = acc[c[0]], r1 = acc[c[1]], r2 = acc[c[2]], r3 = acc[c[3]];
-        r0 = fmaf(a.x, p, r0); r1 = fmaf(a.y, p, r1); r2 = fmaf(a.z, p, r2); r3 = fmaf(a.w, p, r3);
-        if (a.x != 0.0f) acc[c[0]] = r0;
-        if (a.y != 0.0f) acc[c[1]] = r1;
-        if (a.z != 0.0f) acc[c[2]] = r2;
-        if (a.w != 0.0f) acc[c[3]] = r3;
+    auto consume = [&](int s) {
+        if (lane < nv[s]) {
+            const float4 a = ring_v[s * 32 + lane];
+            uint32_t c[4];
+            CI::unpack(ring_i[s * 32 + lane], c);
+            const float p = px[s];
+            // the four columns of a group are distinct (pads use an absent column)
+            float r0 = acc[c[0]], r1 = acc[c[1]], r2 = acc[c[2]], r3 = acc[c[3]];
+            r0 = fmaf(a.x, p, r0); r1 = fmaf(a.y, p, r1); r2 = fmaf(a.z, p, r2); r3 = fmaf(a.w, p, r3);
+            acc[c[0]] = r0; acc[c[1]] = r1; acc[c[2]] = r2; acc[c[3]] = r3;
+        }
         __syncwarp();                                     // next chunk may be another row
     };
 #pragma unroll
-    for (int d = 0; d < kDepth; d++) issue(d);
-    while (lv[0]) {
+    for (int s = 0; s < kStages; s++) issue(s);
+    while (nv[0] > 0) {
 #pragma unroll
-        for (int d = 0; d < kDepth; d++) {
-            if (lv[d]) consume(d);
-            issue(d);
+        for (int s = 0; s < kStages; s++) {
+            cp_async_wait<kStages - 1>();                 // the oldest group (stage s) has landed
+            if (nv[s] > 0) consume(s);
+            issue(s);
         }
     }
+    cp_async_wait<0>();
 
     // ---- fixed-order sum over warps, then over row splits ----------------------------------------
     __syncthreads();
     const int col0 = slab * W;
     const int n_valid = min(W, N - col0);
     const size_t npad = (size_t)gridDim.x * W;
+    const int wstride = warp_smem_bytes<IDXB>(W) / 4;
+    const float *acc0 = reinterpret_cast<const float *>(smem_raw);
     for (int c = tid; c < n_valid; c += kPanelThreads) {
-        float s = acc_all[c];
+        float s = acc0[c];
 #pragma unroll
-        for (int w = 1; w < kPanelWarps; w++) s += acc_all[(size_t)w * W + c];
+        for (int w = 1; w < kPanelWarps; w++) s += acc0[(size_t)w * wstride + c];
         if (splits == 1) y[col0 + c] = s;
         else partial[(size_t)split * npad + col0 + c] = s;
     }
@@ -207,7 +225,7 @@ int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o)
     d.slab_cols = h.slab_cols; d.index_bits = h.index_bits; d.slabs = h.slabs;
     d.row_blocks = h.row_blocks; d.tiled = h.tiled; d.warps = kPanelWarps;
     p->block = kPanelThreads;
-    p->smem = kPanelWarps * h.slab_cols * (int)sizeof(float);
+    p->smem = kPanelWarps * (h.index_bits == 8 ? warp_smem_bytes<8>(h.slab_cols) : warp_smem_bytes<16>(h.slab_cols));
     p->tile_width = h.slab_cols;
     p->col_tiles = h.slabs;
     p->kernels_per_run = 1;

@@ -11,7 +11,7 @@ from types import SimpleNamespace
 
 import numpy as np
 
-from ._cabi import LAYOUTS, VARIANTS, Options, PlanInfo, RefPacked, check, lib
+from ._cabi import LAYOUTS, VARIANTS, Options, PackedDump, PlanInfo, RefPacked, check, lib
 
 
 def _opts(**kw):
@@ -167,4 +167,37 @@ def ref_pack(layout, A):
                           u32=grab(s.u32, s.n_u32, np.uint32), f32=grab(s.f32, s.n_f32, np.float32),
                           aux=list(s.aux))
     lib().spmv_ref_packed_free(C.byref(s))
+    return out
+
+
+def pack_dump(variant, A=None, csc=None, shape=None, **opts):
+    """Host image of the device format (no GPU needed): for the CPU tests of the packers.
+    Pass a dense `A`, or `csc=(col_ptr, row_idx, values)` with `shape=(M, N)`."""
+    d = PackedDump()
+    if A is not None:
+        A = np.ascontiguousarray(A, np.float32)
+        M, N = A.shape
+        check(lib().spmv_pack_dump_dense(VARIANTS[variant], M, N, _ptr(A), max(N, 1), _opts(**opts), C.byref(d)))
+    else:
+        M, N = shape
+        cp = np.ascontiguousarray(csc[0], np.int64)
+        ri = np.ascontiguousarray(csc[1], np.int32)
+        va = np.ascontiguousarray(csc[2], np.float32)
+        check(lib().spmv_pack_dump_csc(VARIANTS[variant], M, N, _ptr(cp), _ptr(ri), _ptr(va), _opts(**opts), C.byref(d)))
+
+    def arr(p, n, dt):
+        if not p or n == 0:
+            return np.zeros(0, dt)
+        return np.ctypeslib.as_array(p, shape=(n,)).astype(dt, copy=True)
+
+    idt = {8: np.uint8, 16: np.uint16, 32: np.uint32}[d.index_bits]
+    nidx = d.idx_bytes // np.dtype(idt).itemsize
+    idx = np.zeros(0, idt)
+    if d.idx and nidx:
+        idx = np.frombuffer(C.string_at(d.idx, d.idx_bytes), dtype=idt).copy()
+    out = SimpleNamespace(variant=variant, index_bits=d.index_bits, slab_cols=d.slab_cols, slabs=d.slabs,
+                          row_blocks=d.row_blocks, M=d.M, N=d.N, nnz=d.nnz, groups=d.groups,
+                          vals=arr(d.vals, d.n_vals, np.float32), idx=idx,
+                          off=arr(d.off, d.n_off, np.uint32), rel=arr(d.rel, d.n_rel, np.uint16))
+    lib().spmv_pack_dump_free(C.byref(d))
     return out

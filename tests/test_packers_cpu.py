@@ -1,0 +1,126 @@
+"""CPU tests of the product's device-format packers through spmv_pack_dump_* (host image of
+what would be uploaded).  The decode below is numpy test code; the product has no CPU SGEMV."""
+import numpy as np
+import pytest
+
+import oracle_bindings as ob
+
+
+def decode_panel(d):
+    """Rebuilds the dense matrix from a dumped AWSP / TCSR image."""
+    A = np.zeros((d.M, d.N), np.float32)
+    W = d.slab_cols
+    vals = d.vals.reshape(-1, 4)
+    idx = d.idx.reshape(-1, 4).astype(np.int64)
+    tiled = d.variant == "tcsr"
+    for s in range(d.slabs):
+        for row in range(d.M):
+            if tiled:
+                rb, r = divmod(row, 32)
+                tb = int(d.off[s * (d.row_blocks + 1) + rb])
+                te = int(d.off[s * (d.row_blocks + 1) + rb + 1])
+                rel = d.rel[(s * d.row_blocks + rb) * 32:(s * d.row_blocks + rb + 1) * 32].astype(np.int64)
+                g0 = tb + rel[r]
+                g1 = tb + rel[r + 1] if r < 31 else te
+            else:
+                g0 = int(d.off[s * (d.M + 1) + row])
+                g1 = int(d.off[s * (d.M + 1) + row + 1])
+            if g1 == g0:
+                continue
+            v = vals[g0:g1].reshape(-1)
+            c = idx[g0:g1].reshape(-1)
+            real = v != 0
+            # pads (value 0) use one column that is absent from the row; real columns are distinct
+            assert not (set(c[~real]) & set(c[real])) and len(set(c[~real])) <= 1
+            assert np.all(c < W)
+            assert np.all(np.diff(c[real]) > 0), "columns ascending inside a segment"
+            A[row, s * W + c[real]] = v[real]
+    return A
+
+
+def decode_wsp(d):
+    A = np.zeros((d.M + 1, d.N), np.float32)      # row M is the pad slot
+    vals = d.vals.reshape(-1, 4)
+    idx = d.idx.reshape(-1, 4).astype(np.int64)
+    for c in range(d.N):
+        g0, g1 = int(d.off[c]), int(d.off[c + 1])
+        v = vals[g0:g1].reshape(-1)
+        r = idx[g0:g1].reshape(-1)
+        assert np.all(r[v == 0] == d.M) and np.all(v[r == d.M] == 0)
+        real = v != 0
+        assert np.all(np.diff(r[real]) > 0), "rows ascending inside a column"
+        A[r[real], c] = v[real]
+    return A[:d.M]
+
+
+CASES = [(64, 32, 0.5), (96, 512, 0.9), (1000, 288, 0.7), (33, 1024, 0.3), (256, 256, 0.0), (128, 64, 1.0)]
+
+
+@pytest.mark.parametrize("M,N,sa", CASES)
+@pytest.mark.parametrize("variant", ["awsp", "tcsr"])
+def test_panel_roundtrip(M, N, sa, variant):
+    import spmv_test_b200 as S
+    A = ob.gen_matrix(M, N, sa, M * 7 + N)
+    d = S.pack_dump(variant, A)
+    assert d.nnz == np.count_nonzero(A) and d.vals.size == 4 * d.groups == d.idx.size
+    assert np.array_equal(decode_panel(d), A)
+    # CSR(A^T) input gives the identical image
+    ptr, idx, val = ob.dense_to_csc(A)
+    e = S.pack_dump(variant, csc=(ptr, idx, val), shape=(M, N))
+    for f in ("vals", "idx", "off", "rel"):
+        assert getattr(d, f).tobytes() == getattr(e, f).tobytes(), f
+
+
+@pytest.mark.parametrize("slab", [256, 512, 1024, 4096])
+def test_panel_slab_widths(slab):
+    import spmv_test_b200 as S
+    A = ob.gen_matrix(160, 4096 + 512, 0.95, slab)
+    for variant in ("awsp", "tcsr"):
+        d = S.pack_dump(variant, A, slab_cols=slab)
+        assert d.slab_cols == slab and d.index_bits == (8 if slab == 256 else 16)
+        assert np.array_equal(decode_panel(d), A)
+
+
+def test_panel_slab_auto_from_density():
+    import spmv_test_b200 as S
+    assert S.pack_dump("awsp", ob.gen_matrix(2048, 2048, 0.7, 1)).slab_cols == 256
+    wide = S.pack_dump("awsp", ob.gen_matrix(4096, 8192, 0.99, 2))
+    assert wide.slab_cols == 4096 and wide.index_bits == 16
+
+
+@pytest.mark.parametrize("M,N,sa", CASES)
+def test_wsp_roundtrip(M, N, sa):
+    import spmv_test_b200 as S
+    A = ob.gen_matrix(M, N, sa, M * 5 + N)
+    d = S.pack_dump("wsp", A)
+    assert d.index_bits == 16 and d.nnz == np.count_nonzero(A)
+    assert np.array_equal(decode_wsp(d), A)
+    d32 = S.pack_dump("wsp", A, index_bits=32)
+    assert d32.index_bits == 32 and np.array_equal(decode_wsp(d32), A)
+    ptr, idx, val = ob.dense_to_csc(A)
+    e = S.pack_dump("wsp", csc=(ptr, idx, val), shape=(M, N))
+    assert d.vals.tobytes() == e.vals.tobytes() and d.idx.tobytes() == e.idx.tobytes() and d.off.tobytes() == e.off.tobytes()
+
+
+def test_rejects_bad_input():
+    import spmv_test_b200 as S
+    with pytest.raises(S.SpmvError):
+        S.pack_dump("awsp", np.zeros((32, 40), np.float32))
+    with pytest.raises(S.SpmvError):
+        S.pack_dump("asp", np.zeros((32, 32), np.float32))
+    ptr = np.array([0, 1] + [1] * 31, np.int64)
+    with pytest.raises(S.SpmvError):      # row index out of range
+        S.pack_dump("awsp", csc=(ptr, np.array([99], np.int32), np.array([1.0], np.float32)), shape=(32, 32))
+
+
+def test_synthetic_generators():
+    from spmv_test_b200 import synth
+    cp, ri, va = synth.bernoulli_csc(4096, 512, 0.01, 3)
+    assert cp[-1] == ri.size == va.size and abs(ri.size / (4096 * 512) - 0.01) < 0.001
+    for c in (0, 17, 511):
+        seg = ri[cp[c]:cp[c + 1]]
+        assert np.all(np.diff(seg) > 0) and (seg.size == 0 or (seg.min() >= 0 and seg.max() < 4096))
+    cp, ri, va = synth.powerlaw_csc(1 << 14, 1 << 14, seed=1)
+    ln = np.diff(cp)
+    assert 10 < ln.mean() < 24 and ln.max() > 20 * ln.mean()
+    assert np.all(va != 0)
