@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libspmv_b200.so")
+# SPMV_B200_LIB: development override (tools/trace_build.sh builds an instrumented library)
+LIB_PATH = os.environ.get("SPMV_B200_LIB") or os.path.join(HERE, "lib", "libspmv_b200.so")
 
 VARIANTS = {"wsp": 0, "asp": 1, "awsp": 2, "tcsr": 3}
 LAYOUTS = {"csr": 0, "tcsr": 1, "wsp": 2, "asp": 3, "awsp": 4, "awsp_ref": 5}

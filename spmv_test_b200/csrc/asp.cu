@@ -7,8 +7,10 @@
 //   * a CTA owns (512-column tile, row range); it first compacts its slice of x into a
 //     shared-memory list of (row, x[row]) with x[row] != 0.0f (asp.cu:23's test, made a pass:
 //     ballot + popc prefix, order preserving), so inactive rows are never addressed;
-//   * every thread owns four adjacent output columns and streams the active rows with
-//     128-bit loads, kAspUnroll rows in flight (a warp reads 512 contiguous bytes per row);
+//   * every thread owns four adjacent output columns; a warp streams its 512 contiguous bytes
+//     of every active row through a private cp.async ring in shared memory, kAspStages rows in
+//     flight per warp (commit/wait groups: a true FIFO, no register or scoreboard limits), and
+//     each lane reads back only the 16 bytes it copied itself, so no barrier is needed;
 //   * row splits are summed in split order by the last CTA to arrive (integer ticket).
 // Deterministic, no floating-point atomics.
 #include <algorithm>
@@ -23,17 +25,18 @@ namespace {
 constexpr int kAspThreads = 128;
 constexpr int kAspTile = kAspThreads * 4;     // output columns per CTA
 constexpr int kAspChunk = 1024;               // rows compacted per pass
-constexpr int kAspUnroll = 8;
+constexpr int kAspStages = 16;             // rows in flight per warp
 
 __global__ void __launch_bounds__(kAspThreads)
 asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ x, float *__restrict__ y,
            float *__restrict__ partial, unsigned *__restrict__ tickets, int M, int N, int rows_per_split,
            int splits)
 {
-    __shared__ int rows_s[kAspChunk];
+    __shared__ __align__(16) int rows_s[kAspChunk];
     __shared__ float xs_s[kAspChunk];
     __shared__ int wcnt[kAspThreads / 32];
     __shared__ int last_flag;
+    __shared__ __align__(16) float4 ring_all[(kAspThreads / 32) * kAspStages * 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x, split = blockIdx.y;
@@ -42,6 +45,7 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
     const int r_begin = split * rows_per_split;
     const int r_end = min(M, r_begin + rows_per_split);
     const float *Ac = A + c0;
+    float4 *ring = ring_all + warp * kAspStages * 32;
 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r0 = r_begin; r0 < r_end; r0 += kAspChunk) {
@@ -81,22 +85,23 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
 
         // ---- stream the active rows ------------------------------------------------------------
         if (col_ok) {
-            for (int i = 0; i < total; i += kAspUnroll) {
-                float4 a[kAspUnroll];
+            auto issue = [&](int i) {
+                if (i < total)
+                    cp_async16(ring + (i & (kAspStages - 1)) * 32 + lane,
+                               Ac + (long long)rows_s[i] * ld);
+                cp_async_commit();
+            };
 #pragma unroll
-                for (int u = 0; u < kAspUnroll; u++) {
-                    if (i + u < total)
-                        a[u] = ldg_stream_f4(reinterpret_cast<const float4 *>(Ac + (long long)rows_s[i + u] * ld));
-                    else
-                        a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < kAspUnroll; u++) {
-                    const float xv = (i + u < total) ? xs_s[i + u] : 0.0f;
-                    acc.x = fmaf(a[u].x, xv, acc.x); acc.y = fmaf(a[u].y, xv, acc.y);
-                    acc.z = fmaf(a[u].z, xv, acc.z); acc.w = fmaf(a[u].w, xv, acc.w);
-                }
+            for (int i = 0; i < kAspStages; i++) issue(i);
+            for (int i = 0; i < total; i++) {
+                cp_async_wait<kAspStages - 1>();          // row i has landed
+                const float4 a = ring[(i & (kAspStages - 1)) * 32 + lane];
+                const float xv = xs_s[i];
+                acc.x = fmaf(a.x, xv, acc.x); acc.y = fmaf(a.y, xv, acc.y);
+                acc.z = fmaf(a.z, xv, acc.z); acc.w = fmaf(a.w, xv, acc.w);
+                issue(i + kAspStages);
             }
+            cp_async_wait<0>();
         }
     }
 
@@ -107,7 +112,9 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
     const size_t npad = (size_t)gridDim.x * kAspTile;
     *reinterpret_cast<float4 *>(partial + (size_t)split * npad + (size_t)tile * kAspTile + tid * 4) = acc;
     const int n_valid = min(kAspTile, N - tile * kAspTile);
-    split_reduce_finish(y, partial, tickets, tile, splits, kAspTile, n_valid, npad, &last_flag);
+    __syncthreads();                                      // the row list is dead: reuse it as scratch
+    split_reduce_finish(y, partial, tickets, tile, splits, kAspTile, n_valid, npad, &last_flag,
+                        reinterpret_cast<float4 *>(rows_s));
 }
 
 } // namespace
@@ -121,7 +128,8 @@ int launch_asp(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st)
     return SPMV_OK;
 }
 
-// grid = (ceil(N/512), row splits): about four CTAs per SM, at least 64 rows per split.
+// grid = (ceil(N/512), row splits): about three CTAs per SM (all resident at once: more splits
+// only add head/tail latency, measured), at least 64 rows per split.
 int configure_asp(spmv_plan *p, const spmv_options_t *o)
 {
     p->block = kAspThreads;
@@ -133,7 +141,7 @@ int configure_asp(spmv_plan *p, const spmv_options_t *o)
     const int64_t M = std::max<int64_t>(p->M, 1);
     int splits;
     if (o && o->row_splits > 0) splits = (int)std::min<int64_t>(o->row_splits, M);
-    else splits = std::max(1, (4 * p->sm_count + p->col_tiles - 1) / std::max(1, p->col_tiles));
+    else splits = std::max(1, (3 * p->sm_count + p->col_tiles / 2) / std::max(1, p->col_tiles));
     int rps = (int)((M + splits - 1) / splits);
     if (!(o && o->row_splits > 0)) rps = std::max(64, rps);
     rps = (rps + 31) / 32 * 32;

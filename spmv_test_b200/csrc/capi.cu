@@ -7,9 +7,14 @@
 #include <cstring>
 #include <new>
 
+#include "common.cuh"
 #include "plan.hpp"
 
 namespace spmv {
+
+#ifdef SPMV_TRACE
+__device__ unsigned long long g_trace[kTraceWarps * kTraceSlots];
+#endif
 
 static thread_local char g_err[512] = "";
 
@@ -308,7 +313,7 @@ int spmv_plan_info(const spmv_plan_t *p, spmv_plan_info_t *info)
     info->index_bits = p->variant == SPMV_WSP ? p->wsp.index_bits
                        : (p->variant == SPMV_ASP ? 0 : p->panel.index_bits);
     info->row_splits = p->row_splits;
-    info->warps_per_col = p->wsp.warps_per_col;
+    info->warps_per_col = p->variant == SPMV_WSP ? p->wsp.warps_per_col : (p->variant == SPMV_ASP ? 4 : p->panel.warps);
     info->slab_cols = (p->variant == SPMV_AWSP || p->variant == SPMV_TCSR) ? p->panel.slab_cols : 0;
     return SPMV_OK;
 }
@@ -407,5 +412,15 @@ int spmv_partition_columns(int64_t N, int parts, int64_t align, const int64_t *c
     bounds[parts] = N;
     return SPMV_OK;
 }
+
+#ifdef SPMV_TRACE
+/* development-only: copy the per-warp timeline out (see common.cuh) */
+SPMV_API int spmv_trace_read(unsigned long long *host, int64_t count)
+{
+    SPMV_CUDA(cudaDeviceSynchronize());
+    SPMV_CUDA(cudaMemcpyFromSymbol(host, spmv::g_trace, sizeof(unsigned long long) * (size_t)count));
+    return SPMV_OK;
+}
+#endif
 
 } // extern "C"

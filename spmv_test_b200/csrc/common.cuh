@@ -5,6 +5,24 @@
 
 namespace spmv {
 
+// ---- development-only timeline (tools/trace_build.sh builds a -DSPMV_TRACE library) -------
+#ifdef SPMV_TRACE
+constexpr int kTraceSlots = 8;
+constexpr int kTraceWarps = 1 << 16;
+extern __device__ unsigned long long g_trace[kTraceWarps * kTraceSlots];
+__device__ __forceinline__ void trace_stamp(int warp_global, int slot)
+{
+    if ((threadIdx.x & 31) == 0 && warp_global < kTraceWarps) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_trace[(size_t)warp_global * kTraceSlots + slot] = t;
+    }
+}
+#define SPMV_STAMP(w, s) ::spmv::trace_stamp((w), (s))
+#else
+#define SPMV_STAMP(w, s) ((void)0)
+#endif
+
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -31,6 +49,12 @@ __device__ __forceinline__ uint2 ldg_stream_u2(const uint2 *p)
     return r;
 }
 
+// fire-and-forget request of one 128-byte line into L2: no register, no scoreboard slot
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -50,6 +74,20 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+// zero-fill forms: copy when `valid`, otherwise write zeros (src-size 0; src must still be a
+// legal address).  Lets a partial chunk stay branch-free.
+__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gmem_src, bool valid)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(valid ? 16 : 0)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async8_zfill(void *smem_dst, const void *gmem_src, bool valid)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(valid ? 8 : 0)
                  : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -119,13 +157,23 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
 
 // ---- cross-CTA fixed-order split reduction -------------------------------------------------
 // Every CTA (tile, split) has written `width` partial sums to partial[split][tile*width ..].
-// The last CTA to arrive for a tile (integer ticket, not a float atomic) adds the splits in
-// ascending split order, so the result does not depend on which CTA happens to be last.
-// Returns true in the CTA that performed the reduction.  All threads of the CTA must call it.
+// The last CTA to arrive for a tile (integer ticket, not a float atomic) adds the splits, so
+// the result does not depend on which CTA happens to be last: with V = width/4 float4 lanes
+// per partial row and K = blockDim/V thread groups, group k adds splits k, k+K, k+2K, ... in
+// ascending order (kRedBatch independent 128-bit loads in flight), then the K group sums are
+// added in group order.  `scratch` needs blockDim.x float4 of shared memory that is free by
+// now.  Returns true in the CTA that performed the reduction.  All threads must call it.
+constexpr int kRedBatch = 8;
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b)
+{
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
 __device__ __forceinline__ bool split_reduce_finish(float *__restrict__ y, const float *__restrict__ partial,
                                                      unsigned *__restrict__ tickets, int tile, int splits,
                                                      int width, int n_valid, size_t split_stride,
-                                                     int *smem_flag)
+                                                     int *smem_flag, float4 *scratch)
 {
     __threadfence();      // publish this CTA's partials
     __syncthreads();
@@ -138,12 +186,36 @@ __device__ __forceinline__ bool split_reduce_finish(float *__restrict__ y, const
     __syncthreads();
     if (!*smem_flag) return false;
     __threadfence();      // acquire the other CTAs' partials
-    for (int c = threadIdx.x; c < width; c += blockDim.x) {
-        if (c >= n_valid) break;
-        const float *p = partial + (size_t)tile * width + c;
-        float acc = 0.0f;
-        for (int s = 0; s < splits; s++) acc += __ldcg(p + (size_t)s * split_stride);
-        y[(size_t)tile * width + c] = acc;
+
+    const int T = blockDim.x, V = width >> 2;
+    const float4 *base = reinterpret_cast<const float4 *>(partial + (size_t)tile * width);
+    const size_t stride4 = split_stride >> 2;
+    auto sum_splits = [&](int v, int first, int step) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = first; s < splits; s += step * kRedBatch) {
+            float4 t[kRedBatch];
+#pragma unroll
+            for (int u = 0; u < kRedBatch; u++) {
+                const int su = s + u * step;
+                t[u] = su < splits ? __ldcg(base + (size_t)su * stride4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < kRedBatch; u++) acc = f4_add(acc, t[u]);
+        }
+        return acc;
+    };
+    float4 *out = reinterpret_cast<float4 *>(y + (size_t)tile * width);
+    if (T >= 2 * V) {
+        const int K = T / V, k = threadIdx.x / V, v = threadIdx.x - k * V;
+        if (k < K) scratch[threadIdx.x] = sum_splits(v, k, K);
+        __syncthreads();
+        if (k == 0 && v * 4 < n_valid) {
+            float4 acc = scratch[v];
+            for (int j = 1; j < K; j++) acc = f4_add(acc, scratch[j * V + v]);
+            out[v] = acc;
+        }
+    } else {
+        for (int v = threadIdx.x; v * 4 < n_valid; v += T) out[v] = sum_splits(v, 0, 1);
     }
     return true;
 }

@@ -30,9 +30,53 @@ static void wsp_finish_layout(HostWsp &w, const std::vector<int64_t> &col_nnz)
     w.colptr[N] = (uint32_t)g;
     w.groups = g;
     w.max_col_groups = mx;
-    w.vals.assign((size_t)g * 4, 0.0f);
-    if (w.index_bits == 16) w.idx16.assign((size_t)g * 4, (uint16_t)w.M);
-    else w.idx32.assign((size_t)g * 4, (uint32_t)w.M);
+    // one spare pad group at the end: the ring kernel may address group `groups` (never uses it)
+    w.vals.assign((size_t)(g + 1) * 4, 0.0f);
+    if (w.index_bits == 16) w.idx16.assign((size_t)(g + 1) * 4, (uint16_t)w.M);
+    else w.idx32.assign((size_t)(g + 1) * 4, (uint32_t)w.M);
+}
+
+// Inside a column the order of the entries is free (any fixed order is deterministic), so it is
+// chosen for the kernel's shared-memory gathers of x: within a chunk of 32 groups the 32 lanes
+// gather element e of their group in one instruction, and the entries are dealt so that those
+// row ids fall into distinct banks (row mod 32) as far as the column allows.
+template <class IdxT> static void wsp_bank_deal(HostWsp &w, std::vector<IdxT> &idx)
+{
+    std::vector<int> bucket[32];
+    std::vector<IdxT> oi(128);
+    std::vector<float> ov(128);
+    for (int64_t c = 0; c < w.N; c++)
+        for (int64_t c0 = w.colptr[c]; c0 < w.colptr[c + 1]; c0 += 32) {
+            const int lanes = (int)std::min<int64_t>(32, w.colptr[c + 1] - c0);
+            const size_t first = (size_t)c0 * 4;
+            const int count = 4 * lanes;
+            for (auto &b : bucket) b.clear();
+            for (int k = 0; k < count; k++) bucket[idx[first + k] & 31].push_back(k);
+            int order[32];
+            for (int b = 0; b < 32; b++) order[b] = b;
+            std::stable_sort(order, order + 32, [&](int a, int b) { return bucket[a].size() > bucket[b].size(); });
+            int fill[4] = {0, 0, 0, 0};
+            for (int t = 0; t < 32; t++) {
+                int mine[4] = {0, 0, 0, 0};
+                for (int k : bucket[order[t]]) {
+                    int best = -1;
+                    for (int e = 0; e < 4; e++) {
+                        if (fill[e] >= lanes) continue;
+                        if (best < 0 || mine[e] < mine[best] || (mine[e] == mine[best] && fill[e] < fill[best])) best = e;
+                    }
+                    oi[4 * fill[best] + best] = idx[first + k];
+                    ov[4 * fill[best] + best] = w.vals[first + k];
+                    fill[best]++; mine[best]++;
+                }
+            }
+            std::copy(oi.begin(), oi.begin() + count, idx.begin() + first);
+            std::copy(ov.begin(), ov.begin() + count, w.vals.begin() + first);
+        }
+}
+
+static void wsp_bank_order(HostWsp &w)
+{
+    if (w.index_bits == 16) wsp_bank_deal(w, w.idx16); else wsp_bank_deal(w, w.idx32);
 }
 
 int pack_wsp_dense(int64_t M, int64_t N, const float *A, int64_t lda, int index_bits, HostWsp &w)
@@ -63,6 +107,7 @@ int pack_wsp_dense(int64_t M, int64_t N, const float *A, int64_t lda, int index_
             }
         }
     }
+    wsp_bank_order(w);
     return SPMV_OK;
 }
 
@@ -94,6 +139,7 @@ int pack_wsp_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *ro
             p++;
         }
     }
+    wsp_bank_order(w);
     return SPMV_OK;
 }
 
@@ -167,25 +213,56 @@ int pack_panel(int64_t M, int64_t N, bool tiled, int W, Source &src, HostPanel &
     const int64_t per_slab = tiled ? (P.row_blocks + 1) : (M + 1);
     P.off.assign((size_t)P.slabs * per_slab, 0);
     if (tiled) P.rel.assign((size_t)P.slabs * P.row_blocks * kTileRows, 0);
-    std::vector<uint16_t> cols((size_t)W);
-    std::vector<float> vals((size_t)W);
+    std::vector<uint16_t> cols((size_t)W + 4);
+    std::vector<float> vals((size_t)W + 4);
 
+    // Inside a segment the order of the entries is free (every column occurs once per row), so
+    // it is chosen for the kernel's shared-memory accumulators: within a chunk of 32 groups the
+    // 32 lanes process element e of their group in the same instruction, and the entries are
+    // dealt so that those columns fall into distinct banks (column mod 32) as far as the row
+    // allows.  Pads carry value 0 and the smallest column ABSENT from the segment: they add an
+    // exact 0 to an accumulator no real entry of this row touches (n % 4 != 0 implies n < W).
+    std::vector<uint16_t> ocols((size_t)W);
+    std::vector<float> ovals((size_t)W);
+    std::vector<int> bucket_of[32];
     auto emit = [&](int n) {
         const int g = (n + 3) / 4;
         const size_t at = P.vals.size();
-        // pads carry value 0 and the smallest column that is ABSENT from the segment, so the
-        // kernel can treat them like real entries: they add an exact 0 to an accumulator no
-        // real entry of this row touches (n % 4 != 0 implies n < W, so such a column exists).
         uint16_t absent = 0;
         for (int k = 0; k < n && cols[k] == absent; k++) absent++;
-        P.vals.resize(at + (size_t)g * 4, 0.0f);
-        std::memcpy(&P.vals[at], vals.data(), sizeof(float) * (size_t)n);
+        for (int k = n; k < 4 * g; k++) { cols[k] = absent; vals[k] = 0.0f; }
+        for (int c0 = 0; c0 < g; c0 += 32) {               // one chunk = up to 32 groups
+            const int lanes = std::min(32, g - c0);
+            const int first = 4 * c0, count = 4 * lanes;
+            for (auto &b : bucket_of) b.clear();
+            for (int k = first; k < first + count; k++) bucket_of[cols[k] & 31].push_back(k);
+            int order[32];
+            for (int b = 0; b < 32; b++) order[b] = b;
+            std::stable_sort(order, order + 32, [&](int a, int b) { return bucket_of[a].size() > bucket_of[b].size(); });
+            int fill[4] = {0, 0, 0, 0};                     // entries dealt to element slot e so far
+            for (int t = 0; t < 32; t++) {                  // largest bank first
+                const std::vector<int> &b = bucket_of[order[t]];
+                int mine[4] = {0, 0, 0, 0};                 // this bank's entries per element slot
+                for (int k : b) {
+                    int best = -1;
+                    for (int e = 0; e < 4; e++) {
+                        if (fill[e] >= lanes) continue;
+                        if (best < 0 || mine[e] < mine[best] || (mine[e] == mine[best] && fill[e] < fill[best])) best = e;
+                    }
+                    ocols[first + 4 * fill[best] + best] = cols[k];
+                    ovals[first + 4 * fill[best] + best] = vals[k];
+                    fill[best]++; mine[best]++;
+                }
+            }
+        }
+        P.vals.resize(at + (size_t)g * 4);
+        std::memcpy(&P.vals[at], ovals.data(), sizeof(float) * (size_t)g * 4);
         if (P.index_bits == 8) {
-            P.idx8.resize(at + (size_t)g * 4, (uint8_t)absent);
-            for (int k = 0; k < n; k++) P.idx8[at + k] = (uint8_t)cols[k];
+            P.idx8.resize(at + (size_t)g * 4);
+            for (int k = 0; k < 4 * g; k++) P.idx8[at + k] = (uint8_t)ocols[k];
         } else {
-            P.idx16.resize(at + (size_t)g * 4, absent);
-            std::memcpy(&P.idx16[at], cols.data(), sizeof(uint16_t) * (size_t)n);
+            P.idx16.resize(at + (size_t)g * 4);
+            std::memcpy(&P.idx16[at], ocols.data(), sizeof(uint16_t) * (size_t)g * 4);
         }
         P.groups += g;
         return g;

@@ -28,8 +28,8 @@ namespace spmv {
 
 namespace {
 
-constexpr int kPanelWarps = 8;
-constexpr int kPanelThreads = kPanelWarps * 32;
+constexpr int kPanelMaxWarps = 8;
+constexpr int kPanelThreads = kPanelMaxWarps * 32;   // launch bound; the CTA size is a plan parameter
 constexpr int kStages = 8;                   // chunks in flight per warp (cp.async groups)
 
 template <int IDXB> struct ColIdx;
@@ -76,12 +76,16 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     using IVec = typename CI::Vec;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_warps = blockDim.x >> 5;
     const int slab = blockIdx.x, split = blockIdx.y;
     unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes<IDXB>(W);
     float *acc = reinterpret_cast<float *>(wbase);
     float4 *ring_v = reinterpret_cast<float4 *>(wbase + (size_t)W * 4);
     IVec *ring_i = reinterpret_cast<IVec *>(wbase + (size_t)W * 4 + kStages * 32 * 16);
     uint4 *meta = reinterpret_cast<uint4 *>(wbase + (size_t)W * 4 + kStages * 32 * 16 + kStages * 32 * sizeof(IVec));
+    const int wg = (blockIdx.y * gridDim.x + blockIdx.x) * n_warps + warp;   // trace id
+    (void)wg;
+    SPMV_STAMP(wg, 0);
     for (int c = lane; c < W; c += 32) acc[c] = 0.0f;
     __syncwarp();
 
@@ -89,24 +93,32 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     int rb_next = split * blocks_per_split + warp;        // block whose metadata is in n*
 
     // ---- metadata of one 32-row block: lane = row ------------------------------------------
-    float nxv = 0.f; uint32_t ng0 = 0, ng1 = 0;
+    // Two blocks of metadata live in registers: A (next to become current) and B (the one
+    // after), so a block's x / offset loads are issued two blocks before they are needed.
+    // (Requesting the segments' lines into L2 ahead of the ring with prefetch.global.L2 was
+    // tried and is slower: every line is one more L1TEX request on an LSU-bound kernel.)
+    struct Meta { float xv; uint32_t g0, g1; };
     auto load_meta = [&](int rb) {
+        Meta m;
         const int row = rb * 32 + lane;
-        nxv = row < M ? __ldg(x + row) : 0.0f;
+        m.xv = row < M ? __ldg(x + row) : 0.0f;
         if (TILED) {
             const size_t t = (size_t)slab * (row_blocks + 1) + rb;
             const uint32_t tb = __ldg(off + t), te = __ldg(off + t + 1);
             const uint32_t r = __ldg(rel + ((size_t)slab * row_blocks + rb) * 32 + lane);
             const uint32_t rn = __shfl_down_sync(kFull, r, 1);
-            ng0 = tb + r;
-            ng1 = lane < 31 ? tb + rn : te;
+            m.g0 = tb + r;
+            m.g1 = lane < 31 ? tb + rn : te;
         } else {
             const size_t o = (size_t)slab * ((size_t)M + 1) + row;
-            ng0 = row < M ? __ldg(off + o) : 0u;
-            ng1 = row < M ? __ldg(off + o + 1) : 0u;
+            m.g0 = row < M ? __ldg(off + o) : 0u;
+            m.g1 = row < M ? __ldg(off + o + 1) : 0u;
         }
+        return m;
     };
-    if (rb_next < rb_end) load_meta(rb_next);
+    Meta mA = {0.f, 0u, 0u}, mB = {0.f, 0u, 0u};
+    if (rb_next < rb_end) mA = load_meta(rb_next);
+    if (rb_next + n_warps < rb_end) mB = load_meta(rb_next + n_warps);
 
     // ---- flat iterator over (block, active row, chunk of 32 groups) ---------------------------
     // The activation compaction: ballot over x != 0 (and a non-empty segment), then an
@@ -117,19 +129,21 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     auto next_row = [&]() {
         while (ri == n_rows) {
             if (rb_next >= rb_end) { live = false; return; }
-            const bool active = nxv != 0.0f && ng1 > ng0;
+            const bool active = mA.xv != 0.0f && mA.g1 > mA.g0;
             const unsigned mask = __ballot_sync(kFull, active);
             __syncwarp();                                 // earlier reads of the list are done
-            if (active) meta[__popc(mask & ((1u << lane) - 1u))] = make_uint4(ng0, ng1, __float_as_uint(nxv), 0u);
+            if (active) meta[__popc(mask & ((1u << lane) - 1u))] = make_uint4(mA.g0, mA.g1, __float_as_uint(mA.xv), 0u);
             __syncwarp();
             n_rows = __popc(mask); ri = 0;
-            rb_next += kPanelWarps;
-            if (rb_next < rb_end) load_meta(rb_next);
+            rb_next += n_warps;
+            mA = mB;                                      // arrived a block ago
+            if (rb_next + n_warps < rb_end) mB = load_meta(rb_next + n_warps);
         }
         const uint4 m = meta[ri++];
         g = m.x; gend = m.y; xv = __uint_as_float(m.z);
     };
     next_row();
+    SPMV_STAMP(wg, 1);
 
     // ---- kStages chunks in flight: cp.async ring, one commit group per chunk -------------------
     float px[kStages]; int nv[kStages];                   // x of the chunk's row, valid lanes
@@ -163,6 +177,9 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     };
 #pragma unroll
     for (int s = 0; s < kStages; s++) issue(s);
+    SPMV_STAMP(wg, 2);
+    cp_async_wait<kStages - 1>();
+    SPMV_STAMP(wg, 3);
     while (nv[0] > 0) {
 #pragma unroll
         for (int s = 0; s < kStages; s++) {
@@ -172,23 +189,27 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         }
     }
     cp_async_wait<0>();
+    SPMV_STAMP(wg, 4);
 
     // ---- fixed-order sum over warps, then over row splits ----------------------------------------
     __syncthreads();
+    SPMV_STAMP(wg, 5);
     const int col0 = slab * W;
     const int n_valid = min(W, N - col0);
     const size_t npad = (size_t)gridDim.x * W;
     const int wstride = warp_smem_bytes<IDXB>(W) / 4;
     const float *acc0 = reinterpret_cast<const float *>(smem_raw);
-    for (int c = tid; c < n_valid; c += kPanelThreads) {
+    for (int c = tid; c < n_valid; c += blockDim.x) {
         float s = acc0[c];
-#pragma unroll
-        for (int w = 1; w < kPanelWarps; w++) s += acc0[(size_t)w * wstride + c];
+        for (int w = 1; w < n_warps; w++) s += acc0[(size_t)w * wstride + c];
         if (splits == 1) y[col0 + c] = s;
         else partial[(size_t)split * npad + col0 + c] = s;
     }
+    SPMV_STAMP(wg, 6);
     if (splits > 1)
-        split_reduce_finish(y, partial, tickets, slab, splits, W, n_valid, npad, &last_flag);
+        split_reduce_finish(y, partial, tickets, slab, splits, W, n_valid, npad, &last_flag,
+                            reinterpret_cast<float4 *>(smem_raw));   // accumulators are dead by now
+    SPMV_STAMP(wg, 7);
 }
 
 template <int IDXB, bool TILED>
@@ -198,7 +219,7 @@ int launch_variant(spmv_plan *p, const float *x, float *y, cudaStream_t st)
     if (p->smem > 48 * 1024)
         SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem));
     const DevPanel &d = p->panel;
-    k<<<p->grid, kPanelThreads, p->smem, st>>>(reinterpret_cast<const float4 *>(d.vals), d.idx, d.off, d.rel, x, y,
+    k<<<p->grid, p->block, p->smem, st>>>(reinterpret_cast<const float4 *>(d.vals), d.idx, d.off, d.rel, x, y,
                                               p->partial, p->tickets, (int)p->M, (int)p->N, d.slab_cols,
                                               d.row_blocks, d.blocks_per_split, p->row_splits);
     SPMV_CUDA(cudaGetLastError());
@@ -223,33 +244,37 @@ int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o)
 {
     DevPanel &d = p->panel;
     d.slab_cols = h.slab_cols; d.index_bits = h.index_bits; d.slabs = h.slabs;
-    d.row_blocks = h.row_blocks; d.tiled = h.tiled; d.warps = kPanelWarps;
-    p->block = kPanelThreads;
-    p->smem = kPanelWarps * (h.index_bits == 8 ? warp_smem_bytes<8>(h.slab_cols) : warp_smem_bytes<16>(h.slab_cols));
+    d.row_blocks = h.row_blocks; d.tiled = h.tiled;
+    // Geometry (measured on B200, profiles/r01_notes.md): about 24 warps per SM in total, every
+    // warp owning at least one 32-row block; 4-warp CTAs when there are many slabs, 8-warp CTAs
+    // when there are few (fewer partial rows to reduce per slab).
+    int warps = h.slabs >= 48 ? 4 : 8;
+    if (o && o->warps_per_col > 0) warps = std::min(kPanelMaxWarps, std::max(1, o->warps_per_col));
+    d.warps = warps;
+    p->block = warps * 32;
+    const int per_warp = h.index_bits == 8 ? warp_smem_bytes<8>(h.slab_cols) : warp_smem_bytes<16>(h.slab_cols);
+    p->smem = warps * per_warp;
     p->tile_width = h.slab_cols;
     p->col_tiles = h.slabs;
     p->kernels_per_run = 1;
 
+    const int smem_cap = p->max_smem_optin > 0 ? p->max_smem_optin : 227 * 1024;
+    if (p->smem > smem_cap)
+        return set_error(SPMV_ERR_UNSUPPORTED, "panel: %d bytes of shared memory exceed the device limit", p->smem);
     const int rb = std::max(1, h.row_blocks);
-    const int resident = std::max(1, std::min(8, (p->max_smem_optin > 0 ? p->max_smem_optin : 227 * 1024) / (p->smem + 1024)));
     const int slabs = std::max(1, h.slabs);
     int splits;
     if (o && o->row_splits > 0) {
         splits = std::min(o->row_splits, rb);
     } else {
-        splits = (rb + 2 * kPanelWarps - 1) / (2 * kPanelWarps);          // two blocks per warp
-        if ((int64_t)splits * slabs < 2 * p->sm_count) splits = (rb + kPanelWarps - 1) / kPanelWarps;
-        // wide slabs: keep the accumulator overhead small against the streamed bytes
-        const int cap = std::max(1, (2 * p->sm_count * resident) / slabs);
-        splits = std::min(splits, cap);
-        splits = std::max(1, std::min(splits, rb));
+        const int target_warps = 24 * p->sm_count;
+        splits = (target_warps + slabs * warps / 2) / (slabs * warps);
+        splits = std::max(1, std::min(splits, (rb + warps - 1) / warps));
     }
     d.blocks_per_split = (rb + splits - 1) / splits;
     splits = (rb + d.blocks_per_split - 1) / d.blocks_per_split;      // no empty splits
     p->row_splits = splits;
     p->grid = dim3((unsigned)slabs, (unsigned)splits, 1);
-    if (p->smem > (p->max_smem_optin > 0 ? p->max_smem_optin : 227 * 1024))
-        return set_error(SPMV_ERR_UNSUPPORTED, "panel: %d bytes of shared memory exceed the device limit", p->smem);
     return alloc_split_scratch(p);
 }
 

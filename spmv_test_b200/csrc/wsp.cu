@@ -143,6 +143,118 @@ wsp_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
     }
 }
 
+// ---- long columns: warp per column, cp.async ring ------------------------------------------
+// A warp walks its columns as one flat sequence of chunks (32 groups = 128 non-zeros); chunk
+// loads go through a private shared-memory ring (kRingStages commit groups in flight: a true
+// FIFO, independent of register and scoreboard limits), partial chunks are zero-filled,
+// x is gathered from shared memory.  The packer
+// deals each chunk's entries so that the 32 lanes' gathers fall into distinct banks.
+constexpr int kRingStages = 8;
+constexpr int kRingWarps = 8;
+
+template <typename IdxVec> struct RingCopy;
+template <> struct RingCopy<uint2> {
+    static __device__ __forceinline__ void copy(uint2 *d, const uint2 *s) { cp_async8(d, s); }
+};
+template <> struct RingCopy<uint4> {
+    static __device__ __forceinline__ void copy(uint4 *d, const uint4 *s) { cp_async16(d, s); }
+};
+
+template <typename IdxVec>
+__global__ void __launch_bounds__(kRingWarps * 32)
+wsp_ring_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
+                const uint32_t *__restrict__ colptr, const int32_t *__restrict__ cols, int ncols,
+                const float *__restrict__ x, float *__restrict__ y, uint32_t M, int x_bulk_ok, int xs_bytes)
+{
+    extern __shared__ __align__(16) unsigned char wsm[];
+    __shared__ __align__(8) uint64_t bar;
+    float *xs = reinterpret_cast<float *>(wsm);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float4 *ring_v = reinterpret_cast<float4 *>(wsm + xs_bytes) + warp * kRingStages * 32;
+    IdxVec *ring_i = reinterpret_cast<IdxVec *>(wsm + xs_bytes + kRingWarps * kRingStages * 32 * 16) + warp * kRingStages * 32;
+
+    // x -> shared memory (1-D bulk async copies when aligned), overlapped with the first chunks
+    const uint32_t m4 = M & ~3u;
+    const bool bulk = x_bulk_ok && m4;
+    if (bulk) {
+        if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, m4 * 4u);
+            for (uint32_t done = 0; done < m4 * 4u; done += 32768u)
+                bulk_g2s(reinterpret_cast<char *>(xs) + done, reinterpret_cast<const char *>(x) + done,
+                         min(m4 * 4u - done, 32768u), &bar);
+        }
+        for (uint32_t j = m4 + tid; j < M; j += blockDim.x) xs[j] = x[j];
+    } else {
+        for (uint32_t j = tid; j < M; j += blockDim.x) xs[j] = x[j];
+    }
+    if (tid < 4) xs[M + tid] = 0.0f;                      // the pad slot
+
+    // ---- flat iterator over (column, chunk) ---------------------------------------------------------
+    const int nwarps = gridDim.x * kRingWarps;
+    int k = blockIdx.x * kRingWarps + warp;               // position in the column list
+    uint32_t g = 0, gend = 0; int ccol = -1; bool live = true;
+    uint32_t n0 = 0, n1 = 0; int ncol = -1;               // next column, prefetched
+    auto fetch_col = [&](int kk) {
+        if (kk < ncols) { ncol = cols ? cols[kk] : kk; n0 = __ldg(colptr + ncol); n1 = __ldg(colptr + ncol + 1); }
+        else ncol = -1;
+    };
+    fetch_col(k);
+    auto next_col = [&]() {
+        if (ncol < 0) { live = false; return; }
+        ccol = ncol; g = n0; gend = n1;
+        k += nwarps;
+        fetch_col(k);
+    };
+    next_col();
+
+    int fin[kRingStages];                                  // >= 0: chunk ends column `fin`; -1: no; -2: empty stage
+    auto issue = [&](int s) {
+        fin[s] = -2;
+        if (live) {
+            const uint32_t gg = g + lane;
+            const bool ok = gg < gend;
+            // lanes past the column's end take value 0 (zero-fill) and the row ids of the
+            // chunk's first group: real rows of this column, so 0 * x[row] adds nothing new
+            const uint32_t gs = ok ? gg : g;
+            cp_async16_zfill(ring_v + s * 32 + lane, vals + gs, ok);
+            RingCopy<IdxVec>::copy(ring_i + s * 32 + lane, idx + gs);
+            g += 32;
+            fin[s] = -1;
+            if (g >= gend) { fin[s] = ccol; next_col(); }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < kRingStages; s++) issue(s);
+
+    if (bulk) mbar_wait(&bar, 0);
+    __syncthreads();                                      // x is in shared memory
+
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    while (fin[0] != -2) {
+#pragma unroll
+        for (int s = 0; s < kRingStages; s++) {
+            cp_async_wait<kRingStages - 1>();
+            if (fin[s] != -2) {
+                const float4 v = ring_v[s * 32 + lane];
+                uint32_t i[4];
+                IdxTraits<IdxVec>::unpack(ring_i[s * 32 + lane], i);
+                a0 = fmaf(v.x, xs[i[0]], a0); a1 = fmaf(v.y, xs[i[1]], a1);
+                a2 = fmaf(v.z, xs[i[2]], a2); a3 = fmaf(v.w, xs[i[3]], a3);
+                if (fin[s] >= 0) {
+                    const float t = warp_sum((a0 + a1) + (a2 + a3));
+                    if (lane == 0) y[fin[s]] = t;
+                    a0 = a1 = a2 = a3 = 0.f;
+                }
+            }
+            issue(s);
+        }
+    }
+    cp_async_wait<0>();
+}
+
 struct Bin { int T; std::vector<int32_t> cols; };
 
 } // namespace
@@ -150,7 +262,7 @@ struct Bin { int T; std::vector<int32_t> cols; };
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-struct WspBinDev { int T; int32_t *cols; int ncols; int grid; };
+struct WspBinDev { int T; int32_t *cols; int ncols; int grid; bool ring; int smem; };
 
 struct WspState {            // hangs off the plan through plan->wsp_state
     std::vector<WspBinDev> bins;
@@ -185,6 +297,18 @@ static int launch_T(const spmv_plan *p, const WspBinDev &b, const float *x, floa
     return set_error(SPMV_ERR_ARG, "wsp: bad team size %d", b.T);
 }
 
+template <typename IdxVec>
+static int launch_ring(const spmv_plan *p, const WspBinDev &b, const float *x, float *y, cudaStream_t st, int ok)
+{
+    auto k = wsp_ring_kernel<IdxVec>;
+    if (b.smem > 48 * 1024) SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, b.smem));
+    k<<<b.grid, kRingWarps * 32, b.smem, st>>>(reinterpret_cast<const float4 *>(p->wsp.vals),
+                                              reinterpret_cast<const IdxVec *>(p->wsp.idx), p->wsp.colptr, b.cols,
+                                              b.ncols, x, y, (uint32_t)p->M, ok, p->smem);
+    SPMV_CUDA(cudaGetLastError());
+    return SPMV_OK;
+}
+
 int launch_wsp(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st)
 {
     if (p->N == 0) return SPMV_OK;
@@ -192,6 +316,12 @@ int launch_wsp(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st)
     const int ok = ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) ? 1 : 0;
     for (const WspBinDev &b : s->bins) {
         int rc;
+        if (b.ring) {
+            if (p->wsp.index_bits == 16) rc = launch_ring<uint2>(p, b, d_x, d_y, st, ok);
+            else rc = launch_ring<uint4>(p, b, d_x, d_y, st, ok);
+            if (rc) return rc;
+            continue;
+        }
         const size_t smem = p->wsp.x_in_smem ? (size_t)p->smem : 0;
         if (p->wsp.index_bits == 16)
             rc = p->wsp.x_in_smem ? launch_T<uint2, true>(p, b, d_x, d_y, st, smem, ok)
@@ -262,6 +392,15 @@ int configure_wsp(spmv_plan *p, const HostWsp &w, const spmv_options_t *o)
         const int teams_per_cta = kWspBlock / b.T;
         const int64_t need = ((int64_t)d.ncols + teams_per_cta - 1) / teams_per_cta;
         d.grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)p->sm_count * ctas_per_sm));
+        d.ring = false; d.smem = 0;
+        if (p->wsp.x_in_smem && b.T >= 32 && !(o && o->warps_per_col > 0)) {
+            // long columns: warp per column through the cp.async ring
+            d.ring = true;
+            d.smem = p->smem + kRingWarps * kRingStages * 32 * (16 + (w.index_bits == 16 ? 8 : 16));
+            const int resident = std::max(1, std::min(8, (220 * 1024) / (d.smem + 1024)));
+            const int64_t want = ((int64_t)d.ncols + kRingWarps - 1) / kRingWarps;
+            d.grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * resident));
+        }
         s->bins.push_back(d);
     }
     p->kernels_per_run = (int)s->bins.size();

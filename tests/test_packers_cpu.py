@@ -33,7 +33,14 @@ def decode_panel(d):
             # pads (value 0) use one column that is absent from the row; real columns are distinct
             assert not (set(c[~real]) & set(c[real])) and len(set(c[~real])) <= 1
             assert np.all(c < W)
-            assert np.all(np.diff(c[real]) > 0), "columns ascending inside a segment"
+            assert len(set(c[real])) == int(real.sum()), "a column occurs once per segment"
+            # bank-aware order: within a chunk of 32 groups, element e of the lanes hits distinct
+            # banks unless some bank holds more than four of the row's columns
+            for q0 in range(0, g1 - g0, 32):
+                blk = idx[g0 + q0:g0 + min(q0 + 32, g1 - g0)]
+                worst = max(np.bincount(blk[:, e] % 32).max() for e in range(4))
+                need = -(-np.bincount(blk.reshape(-1) % 32).max() // 4)
+                assert worst <= max(need, 1) + 1
             A[row, s * W + c[real]] = v[real]
     return A
 
@@ -42,13 +49,14 @@ def decode_wsp(d):
     A = np.zeros((d.M + 1, d.N), np.float32)      # row M is the pad slot
     vals = d.vals.reshape(-1, 4)
     idx = d.idx.reshape(-1, 4).astype(np.int64)
+    assert vals.shape[0] == d.groups + 1 and np.all(vals[-1] == 0) and np.all(idx[-1] == d.M)   # spare pad group
     for c in range(d.N):
         g0, g1 = int(d.off[c]), int(d.off[c + 1])
         v = vals[g0:g1].reshape(-1)
         r = idx[g0:g1].reshape(-1)
         assert np.all(r[v == 0] == d.M) and np.all(v[r == d.M] == 0)
         real = v != 0
-        assert np.all(np.diff(r[real]) > 0), "rows ascending inside a column"
+        assert len(set(r[real])) == int(real.sum()), "a row occurs once per column"
         A[r[real], c] = v[real]
     return A[:d.M]
 
@@ -93,7 +101,7 @@ def test_wsp_roundtrip(M, N, sa):
     import spmv_test_b200 as S
     A = ob.gen_matrix(M, N, sa, M * 5 + N)
     d = S.pack_dump("wsp", A)
-    assert d.index_bits == 16 and d.nnz == np.count_nonzero(A)
+    assert d.index_bits == 16 and d.nnz == np.count_nonzero(A) and d.vals.size == 4 * (d.groups + 1)
     assert np.array_equal(decode_wsp(d), A)
     d32 = S.pack_dump("wsp", A, index_bits=32)
     assert d32.index_bits == 32 and np.array_equal(decode_wsp(d32), A)
