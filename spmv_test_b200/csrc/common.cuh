@@ -84,6 +84,12 @@ __device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gme
                  "r"(valid ? 16 : 0)
                  : "memory");
 }
+__device__ __forceinline__ void cp_async4_zfill(void *smem_dst, const void *gmem_src, bool valid)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(valid ? 4 : 0)
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async8_zfill(void *smem_dst, const void *gmem_src, bool valid)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),

@@ -293,16 +293,19 @@ int pack_panel(int64_t M, int64_t N, bool tiled, int W, Source &src, HostPanel &
 }
 } // namespace
 
-// Slab width from the density: aim at ~100 non-zeros per row segment so the 128-bit group
-// padding, the per-segment offsets and the DRAM sector fringe stay a few percent; 8-bit
-// columns (slab 256) whenever the density allows it.
+// Slab width from the density.  DRAM wants long contiguous pieces (measured on B200,
+// tools/ubench/bulk_vs_ldgsts.cu: 400-byte segments with equal gaps stream at 3.5 TB/s, >= 1 KB
+// pieces at 6.4 TB/s) and full 32-group chunks keep the lanes busy, so aim at ~300 non-zeros per
+// row segment; but keep at least ~1000 (slab, 32-row block) work units so a small matrix still
+// spreads over the SMs.  256-wide slabs use 8-bit column ids, wider ones 16-bit.
 int choose_slab_cols(int64_t M, int64_t N, int64_t nnz)
 {
     if (M <= 0 || N <= 0 || nnz <= 0) return kMinSlabCols;
     const double density = (double)nnz / ((double)M * (double)N);
-    if (density >= 0.125) return 256;
-    int w = 512;
-    while (w < kMaxSlabCols && w * density < 100.0) w <<= 1;
+    int w = kMinSlabCols;
+    while (w < kMaxSlabCols && w * density < 300.0) w <<= 1;
+    const int64_t row_blocks = (M + kTileRows - 1) / kTileRows;
+    while (w > kMinSlabCols && ((N + w - 1) / w) * row_blocks < 1024) w >>= 1;
     return w;
 }
 
