@@ -69,6 +69,16 @@ int alloc_split_scratch(spmv_plan *p)
     return SPMV_OK;
 }
 
+int alloc_panel_scratch(spmv_plan *p, size_t partial_floats, size_t tickets)
+{
+    int rc = dev_alloc(p, &p->partial, partial_floats, false);
+    if (rc) return rc;
+    rc = dev_alloc(p, &p->tickets, tickets, true);
+    if (rc) return rc;
+    p->scratch_bytes += (int64_t)(partial_floats * sizeof(float) + tickets * sizeof(unsigned));
+    return SPMV_OK;
+}
+
 static int plan_begin(int variant, int64_t M, int64_t N, spmv_plan **out)
 {
     if (!out) return set_error(SPMV_ERR_ARG, "null output pointer");
@@ -325,7 +335,9 @@ int spmv_plan_traffic(const spmv_plan_t *p, const float *x, double *alg_bytes, d
     if (!x && p->M > 0 && p->variant != SPMV_WSP) return set_error(SPMV_ERR_ARG, "x is null");
     const double M = (double)p->M, N = (double)p->N;
     const double vec = 4.0 * M + 4.0 * N;
-    const double split_io = p->row_splits > 1 ? 2.0 * 4.0 * p->row_splits * (double)p->col_tiles * p->tile_width : 0.0;
+    double split_io = p->row_splits > 1 ? 2.0 * 4.0 * p->row_splits * (double)p->col_tiles * p->tile_width : 0.0;
+    if (p->variant == SPMV_AWSP || p->variant == SPMV_TCSR)      // one partial row per CTA piece, written + read
+        split_io = 2.0 * 4.0 * ((double)p->grid.x + p->col_tiles) * p->tile_width;
     double alg = 0, phys = 0;
     int64_t touched = 0;
     if (p->variant == SPMV_WSP) {

@@ -162,13 +162,14 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
 }
 
 // ---- cross-CTA fixed-order split reduction -------------------------------------------------
-// Every CTA (tile, split) has written `width` partial sums to partial[split][tile*width ..].
-// The last CTA to arrive for a tile (integer ticket, not a float atomic) adds the splits, so
-// the result does not depend on which CTA happens to be last: with V = width/4 float4 lanes
-// per partial row and K = blockDim/V thread groups, group k adds splits k, k+K, k+2K, ... in
-// ascending order (kRedBatch independent 128-bit loads in flight), then the K group sums are
-// added in group order.  `scratch` needs blockDim.x float4 of shared memory that is free by
-// now.  Returns true in the CTA that performed the reduction.  All threads must call it.
+// Several CTAs have each written one partial row (`width` floats) for an output tile.  The
+// last one to arrive (integer ticket, not a float atomic) adds the rows, so the result does
+// not depend on which CTA happens to be last: with V = width/4 float4 lanes per row and
+// K = blockDim/V thread groups, group k adds rows k, k+K, k+2K, ... in ascending order
+// (kRedBatch independent 128-bit loads in flight), then the K group sums are added in group
+// order.  `row(j)` returns the j-th partial row (16-byte aligned); `scratch` needs blockDim.x
+// float4 of shared memory that is free by now.  Returns true in the CTA that performed the
+// reduction.  All threads of the CTA must call it.
 constexpr int kRedBatch = 8;
 
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b)
@@ -176,44 +177,41 @@ __device__ __forceinline__ float4 f4_add(float4 a, float4 b)
     return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
 
-__device__ __forceinline__ bool split_reduce_finish(float *__restrict__ y, const float *__restrict__ partial,
-                                                     unsigned *__restrict__ tickets, int tile, int splits,
-                                                     int width, int n_valid, size_t split_stride,
-                                                     int *smem_flag, float4 *scratch)
+template <class RowFn>
+__device__ __forceinline__ bool split_reduce_rows(float *__restrict__ y_tile, RowFn row, unsigned *__restrict__ ticket,
+                                                  int rows, int width, int n_valid, int *smem_flag, float4 *scratch)
 {
-    __threadfence();      // publish this CTA's partials
+    __threadfence();      // publish this CTA's partial row
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned t = atomicAdd(&tickets[tile], 1u);
-        int last = (t == (unsigned)(splits - 1));
-        if (last) tickets[tile] = 0; // re-arm for the next call / graph replay
+        unsigned t = atomicAdd(ticket, 1u);
+        int last = (t == (unsigned)(rows - 1));
+        if (last) *ticket = 0; // re-arm for the next call / graph replay
         *smem_flag = last;
     }
     __syncthreads();
     if (!*smem_flag) return false;
-    __threadfence();      // acquire the other CTAs' partials
+    __threadfence();      // acquire the other CTAs' partial rows
 
     const int T = blockDim.x, V = width >> 2;
-    const float4 *base = reinterpret_cast<const float4 *>(partial + (size_t)tile * width);
-    const size_t stride4 = split_stride >> 2;
-    auto sum_splits = [&](int v, int first, int step) {
+    auto sum_rows = [&](int v, int first, int step) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = first; s < splits; s += step * kRedBatch) {
+        for (int s = first; s < rows; s += step * kRedBatch) {
             float4 t[kRedBatch];
 #pragma unroll
             for (int u = 0; u < kRedBatch; u++) {
                 const int su = s + u * step;
-                t[u] = su < splits ? __ldcg(base + (size_t)su * stride4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+                t[u] = su < rows ? __ldcg(reinterpret_cast<const float4 *>(row(su)) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < kRedBatch; u++) acc = f4_add(acc, t[u]);
         }
         return acc;
     };
-    float4 *out = reinterpret_cast<float4 *>(y + (size_t)tile * width);
+    float4 *out = reinterpret_cast<float4 *>(y_tile);
     if (T >= 2 * V) {
         const int K = T / V, k = threadIdx.x / V, v = threadIdx.x - k * V;
-        if (k < K) scratch[threadIdx.x] = sum_splits(v, k, K);
+        if (k < K) scratch[threadIdx.x] = sum_rows(v, k, K);
         __syncthreads();
         if (k == 0 && v * 4 < n_valid) {
             float4 acc = scratch[v];
@@ -221,9 +219,20 @@ __device__ __forceinline__ bool split_reduce_finish(float *__restrict__ y, const
             out[v] = acc;
         }
     } else {
-        for (int v = threadIdx.x; v * 4 < n_valid; v += T) out[v] = sum_splits(v, 0, 1);
+        for (int v = threadIdx.x; v * 4 < n_valid; v += T) out[v] = sum_rows(v, 0, 1);
     }
     return true;
+}
+
+// regular layout: partial[split][tile*width ..], split stride `split_stride` floats
+__device__ __forceinline__ bool split_reduce_finish(float *__restrict__ y, const float *__restrict__ partial,
+                                                     unsigned *__restrict__ tickets, int tile, int splits,
+                                                     int width, int n_valid, size_t split_stride,
+                                                     int *smem_flag, float4 *scratch)
+{
+    const float *base = partial + (size_t)tile * width;
+    return split_reduce_rows(y + (size_t)tile * width, [&](int j) { return base + (size_t)j * split_stride; },
+                             &tickets[tile], splits, width, n_valid, smem_flag, scratch);
 }
 
 } // namespace spmv

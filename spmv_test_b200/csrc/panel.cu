@@ -59,19 +59,30 @@ template <> struct ColIdx<16> {
     static __device__ __forceinline__ Vec zero() { return make_uint2(0u, 0u); }
 };
 
-// per-warp shared memory: [acc: W floats][vals ring: kStages x 32 float4][idx ring][meta: 32 x uint4][slot info]
+// per-warp shared memory: [acc: W floats][vals ring: kStages x 32 float4][idx ring][list: 64 x uint4][slot info]
+constexpr int kListCap = 128;              // rows a warp can take from one metadata batch
+constexpr int kMetaBatch = 4;              // 32-row blocks of metadata fetched together
 template <int IDXB> __host__ __device__ constexpr int warp_smem_bytes(int W)
 {
-    return W * 4 + kStages * 32 * 16 + kStages * 32 * (IDXB == 8 ? 4 : 8) + 32 * 16 + kStages * 8;
+    return W * 4 + kStages * 32 * 16 + kStages * 32 * (IDXB == 8 ? 4 : 8) + kListCap * 16 + kStages * 8;
 }
+
+// Balanced flat decomposition.  The (slab, row) pairs, slab-major, form one sequence of
+// T = slabs*M units; CTA c of G owns units [c*T/G, (c+1)*T/G): equal work for every CTA whatever
+// the slab count, one resident wave.  A range that crosses a slab boundary is processed as
+// consecutive *pieces* (slab, row range); every piece ends with a fixed-order sum of the CTA's
+// warps into one partial row, and the last piece to arrive for a slab (integer ticket) adds that
+// slab's partial rows in CTA order.  The decomposition depends only on (shape, G), so a plan
+// always reproduces its results bit for bit.
+__device__ __forceinline__ long long range_begin(long long c, long long T, long long G) { return c * T / G; }
+__device__ __forceinline__ long long cta_of_unit(long long u, long long T, long long G) { return ((u + 1) * G - 1) / T; }
 
 template <int IDXB, bool TILED>
 __global__ void __launch_bounds__(kPanelThreads)
 panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
              const uint32_t *__restrict__ off, const uint16_t *__restrict__ rel,
              const float *__restrict__ x, float *__restrict__ y, float *__restrict__ partial,
-             unsigned *__restrict__ tickets, int M, int N, int W, int row_blocks,
-             int blocks_per_split, int splits)
+             unsigned *__restrict__ tickets, int M, int N, int W, int row_blocks, int slabs, int kmax)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int last_flag;
@@ -80,29 +91,23 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_warps = blockDim.x >> 5;
-    const int slab = blockIdx.x, split = blockIdx.y;
+    const unsigned lt = (1u << lane) - 1u;
     unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes<IDXB>(W);
     float *acc = reinterpret_cast<float *>(wbase);
     float4 *ring_v = reinterpret_cast<float4 *>(wbase + (size_t)W * 4);
     IVec *ring_i = reinterpret_cast<IVec *>(wbase + (size_t)W * 4 + kStages * 32 * 16);
-    uint4 *meta = reinterpret_cast<uint4 *>(wbase + (size_t)W * 4 + kStages * 32 * 16 + kStages * 32 * sizeof(IVec));
-    uint2 *sinfo = reinterpret_cast<uint2 *>(meta + 32);   // per ring slot: (valid lanes, x of the row)
-    const int wg = (blockIdx.y * gridDim.x + blockIdx.x) * n_warps + warp;   // trace id
+    uint4 *list = reinterpret_cast<uint4 *>(wbase + (size_t)W * 4 + kStages * 32 * 16 + kStages * 32 * sizeof(IVec));
+    uint2 *sinfo = reinterpret_cast<uint2 *>(list + kListCap);   // per ring slot: (valid lanes, x of the row)
+    const int wg = blockIdx.x * n_warps + warp;           // trace id
     (void)wg;
     SPMV_STAMP(wg, 0);
-    for (int c = lane; c < W; c += 32) acc[c] = 0.0f;
-    __syncwarp();
 
-    const int rb_end = min(row_blocks, (split + 1) * blocks_per_split);
-    const int rb_first = split * blocks_per_split + warp; // this warp's blocks: rb_first, +n_warps, ...
+    const long long T = (long long)slabs * M, G = gridDim.x;
+    const long long u_begin = range_begin(blockIdx.x, T, G), u_end = range_begin(blockIdx.x + 1, T, G);
 
-    // ---- metadata of one 32-row block: lane = row ------------------------------------------
-    // Two blocks of metadata live in registers: A (next to become current) and B (the one
-    // after), so a block's x / offset loads are issued two blocks before they are needed.
-    // (Requesting the segments' lines into L2 ahead of the ring with prefetch.global.L2 was
-    // tried and is slower: every line is one more L1TEX request on an LSU-bound kernel.)
+    // ---- metadata of one 32-row block of a slab: lane = row ---------------------------------------
     struct Meta { float xv; uint32_t g0, g1; };
-    auto load_meta = [&](int rb) {
+    auto load_meta = [&](int slab, int rb) {
         Meta m;
         const int row = rb * 32 + lane;
         m.xv = row < M ? __ldg(x + row) : 0.0f;
@@ -120,21 +125,14 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         }
         return m;
     };
-    Meta mA = {0.f, 0u, 0u}, mB = {0.f, 0u, 0u};
-    if (rb_first < rb_end) mA = load_meta(rb_first);
-    if (rb_first + n_warps < rb_end) mB = load_meta(rb_first + n_warps);
 
     // ---- kStages chunks in flight: cp.async ring, one commit group per chunk -------------------
-    // The (block, active row, chunk of 32 groups) nest below is one flat sequence of chunks to
-    // the ring: `step` first retires the oldest slot (read-modify-write of the accumulator row),
-    // then refills it with the chunk at hand.  Branch-free per chunk: lanes past the segment's
-    // end zero-fill their slots, compute like everyone and only their stores are predicated off,
-    // so an idle lane can never overwrite a live lane's update.  Slot info (valid lanes, x of
-    // the row) sits next to the ring; everything starts zeroed, so the warm-up steps and the
-    // final drain are the same code.
-    for (int k = lane; k < kStages * 32; k += 32) ring_i[k] = CI::zero();
-    if (lane < kStages) sinfo[lane] = make_uint2(0u, 0u);
-    __syncwarp();
+    // A warp's rows form one flat sequence of chunks (32 groups) to the ring: `retire` finishes
+    // the oldest slot (read-modify-write of the accumulator row), then the slot is refilled with
+    // the chunk at hand.  Branch-free per chunk: lanes past the segment's end zero-fill their
+    // slots, compute like everyone and only their stores are predicated off, so an idle lane can
+    // never overwrite a live lane's update.  Slot info (valid lanes, x of the row) sits next to
+    // the ring; a piece starts with everything zeroed, so warm-up and drain are the same code.
     int it = 0;
     auto retire = [&](int s) {
         const uint2 info = sinfo[s];
@@ -148,24 +146,9 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         if (lane < info.x) { acc[c[0]] = r0; acc[c[1]] = r1; acc[c[2]] = r2; acc[c[3]] = r3; }
         __syncwarp();                                     // next chunk may be another row
     };
-
-    bool stamped = false; (void)stamped;
-    for (int rb = split * blocks_per_split + warp; rb < rb_end; rb += n_warps) {
-        // activation compaction of this block: ballot over x != 0 (and a non-empty segment),
-        // then an order-preserving popc scatter of (first group, end group, x) into the list
-        const bool active = mA.xv != 0.0f && mA.g1 > mA.g0;
-        const unsigned mask = __ballot_sync(kFull, active);
-        if (active) meta[__popc(mask & ((1u << lane) - 1u))] = make_uint4(mA.g0, mA.g1, __float_as_uint(mA.xv), 0u);
-        __syncwarp();
-        const int n_rows = __popc(mask);
-        mA = mB;                                          // issued two blocks ago
-        if (rb + 2 * n_warps < rb_end) mB = load_meta(rb + 2 * n_warps);
-#ifdef SPMV_TRACE
-        if (!stamped) { SPMV_STAMP(wg, 1); stamped = true; }
-#endif
+    auto run_list = [&](int n_rows) {
         for (int r = 0; r < n_rows; r++) {
-            const uint4 m = meta[r];
-            const float xv = __uint_as_float(m.z);
+            const uint4 m = list[r];
 #pragma unroll 1
             for (uint32_t g = m.x; g < m.y; g += 32) {
                 const int s = it++ & (kStages - 1);
@@ -180,34 +163,98 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
                 if (lane == 0) sinfo[s] = make_uint2(min(32u, m.y - g), m.z);
             }
         }
-        __syncwarp();                                     // the list is rewritten next
-    }
-    SPMV_STAMP(wg, 2);
-    cp_async_wait<0>();
-    SPMV_STAMP(wg, 3);
-#pragma unroll 1
-    for (int k = 0; k < kStages; k++) retire(it++ & (kStages - 1));
-    SPMV_STAMP(wg, 4);
+    };
 
-    // ---- fixed-order sum over warps, then over row splits ----------------------------------------
-    __syncthreads();
-    SPMV_STAMP(wg, 5);
-    const int col0 = slab * W;
-    const int n_valid = min(W, N - col0);
-    const size_t npad = (size_t)gridDim.x * W;
-    const int wstride = warp_smem_bytes<IDXB>(W) / 4;
-    const float *acc0 = reinterpret_cast<const float *>(smem_raw);
-    for (int c = tid; c < n_valid; c += blockDim.x) {
-        float s = acc0[c];
-        for (int w = 1; w < n_warps; w++) s += acc0[(size_t)w * wstride + c];
-        if (splits == 1) y[col0 + c] = s;
-        else partial[(size_t)split * npad + col0 + c] = s;
+    int piece = 0;
+    for (long long u = u_begin; u < u_end; piece++) {
+        const int slab = (int)(u / M);
+        const int row_a = (int)(u - (long long)slab * M);
+        const int row_b = (int)min((long long)M, row_a + (u_end - u));
+        u += row_b - row_a;
+
+        for (int c = lane; c < W; c += 32) acc[c] = 0.0f;
+        for (int k = lane; k < kStages * 32; k += 32) ring_i[k] = CI::zero();
+        if (lane < kStages) sinfo[lane] = make_uint2(0u, 0u);
+        __syncwarp();
+
+        // activation compaction: every warp looks at every 32-row block of the piece (lane =
+        // row): ballot over "in range, x != 0, segment non-empty", order-preserving popc rank;
+        // warp w keeps the active rows whose rank is w modulo the warp count, so the warps of
+        // a CTA end up with equal shares whatever the piece length.
+        // Metadata is fetched kMetaBatch blocks at a time, one batch ahead of its use, so its
+        // latency is paid once per 128 rows and overlaps the previous batch's streaming.
+        const int blk_a = row_a >> 5, blk_b = (row_b + 31) >> 5;
+        int rank_base = 0;
+        Meta nxt[kMetaBatch];
+#pragma unroll
+        for (int j = 0; j < kMetaBatch; j++)
+            if (blk_a + j < blk_b) nxt[j] = load_meta(slab, blk_a + j);
+        for (int blk0 = blk_a; blk0 < blk_b; blk0 += kMetaBatch) {
+            Meta cur[kMetaBatch];
+#pragma unroll
+            for (int j = 0; j < kMetaBatch; j++) cur[j] = nxt[j];
+#pragma unroll
+            for (int j = 0; j < kMetaBatch; j++)
+                if (blk0 + kMetaBatch + j < blk_b) nxt[j] = load_meta(slab, blk0 + kMetaBatch + j);
+            int cnt = 0;
+#pragma unroll
+            for (int j = 0; j < kMetaBatch; j++) {
+                const int row = (blk0 + j) * 32 + lane;
+                const bool valid = blk0 + j < blk_b && row >= row_a && row < row_b && cur[j].xv != 0.0f && cur[j].g1 > cur[j].g0;
+                const unsigned mask = __ballot_sync(kFull, valid);
+                const int rank = rank_base + __popc(mask & lt);
+                const bool mine = valid && (rank & (n_warps - 1)) == warp;   // n_warps is a power of two
+                const unsigned mm = __ballot_sync(kFull, mine);
+                if (mine) list[cnt + __popc(mm & lt)] = make_uint4(cur[j].g0, cur[j].g1, __float_as_uint(cur[j].xv), 0u);
+                cnt += __popc(mm);
+                rank_base += __popc(mask);
+            }
+            __syncwarp();
+            if (piece == 0 && blk0 == blk_a) SPMV_STAMP(wg, 1);
+            run_list(cnt);
+            __syncwarp();                                 // the list is rewritten next
+        }
+        SPMV_STAMP(wg, 2);
+        cp_async_wait<0>();
+        SPMV_STAMP(wg, 3);
+#pragma unroll 1
+        for (int k = 0; k < kStages; k++) retire(it++ & (kStages - 1));
+        SPMV_STAMP(wg, 4);
+
+        // ---- fixed-order sum over warps, then over the slab's pieces -----------------------------
+        __syncthreads();
+        SPMV_STAMP(wg, 5);
+        const long long s_begin = (long long)slab * M;
+        const long long c_lo = cta_of_unit(s_begin, T, G), c_hi = cta_of_unit(s_begin + M - 1, T, G);
+        const int n_pieces = (int)(c_hi - c_lo + 1);
+        const int col0 = slab * W;
+        const int n_valid = min(W, N - col0);
+        const int wstride = warp_smem_bytes<IDXB>(W) / 4;
+        const float *acc0 = reinterpret_cast<const float *>(smem_raw);
+        float *dst = n_pieces == 1 ? y + col0 : partial + ((size_t)blockIdx.x * kmax + piece) * W;
+        for (int c = tid; c < n_valid; c += blockDim.x) {
+            float s = acc0[c];
+            for (int w = 1; w < n_warps; w++) s += acc0[(size_t)w * wstride + c];
+            dst[c] = s;
+        }
+        SPMV_STAMP(wg, 6);
+        if (n_pieces > 1) {
+            // partial row j of this slab was written by CTA c_lo + j as its piece number
+            // (slab - first slab of that CTA); the row offsets go to shared memory once
+            float4 *scratch = reinterpret_cast<float4 *>(smem_raw);          // accumulators are dead by now
+            uint32_t *row_of = reinterpret_cast<uint32_t *>(scratch + blockDim.x);
+            __syncthreads();
+            for (int j = tid; j < n_pieces; j += blockDim.x) {
+                const long long c = c_lo + j;
+                row_of[j] = (uint32_t)(c * kmax + (slab - (int)(range_begin(c, T, G) / M)));
+            }
+            // (split_reduce_rows starts with a barrier, which also publishes row_of)
+            split_reduce_rows(y + col0, [&](int j) { return partial + (size_t)row_of[j] * W; }, &tickets[slab],
+                              n_pieces, W, n_valid, &last_flag, scratch);
+        }
+        __syncthreads();                                  // shared memory is reused by the next piece
+        SPMV_STAMP(wg, 7);
     }
-    SPMV_STAMP(wg, 6);
-    if (splits > 1)
-        split_reduce_finish(y, partial, tickets, slab, splits, W, n_valid, npad, &last_flag,
-                            reinterpret_cast<float4 *>(smem_raw));   // accumulators are dead by now
-    SPMV_STAMP(wg, 7);
 }
 
 template <int IDXB, bool TILED>
@@ -218,8 +265,8 @@ int launch_variant(spmv_plan *p, const float *x, float *y, cudaStream_t st)
         SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem));
     const DevPanel &d = p->panel;
     k<<<p->grid, p->block, p->smem, st>>>(reinterpret_cast<const float4 *>(d.vals), d.idx, d.off, d.rel, x, y,
-                                              p->partial, p->tickets, (int)p->M, (int)p->N, d.slab_cols,
-                                              d.row_blocks, d.blocks_per_split, p->row_splits);
+                                         p->partial, p->tickets, (int)p->M, (int)p->N, d.slab_cols,
+                                         d.row_blocks, d.slabs, d.kmax);
     SPMV_CUDA(cudaGetLastError());
     return SPMV_OK;
 }
@@ -229,69 +276,55 @@ int launch_variant(spmv_plan *p, const float *x, float *y, cudaStream_t st)
 int launch_panel(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st)
 {
     if (p->N == 0) return SPMV_OK;
+    if (p->M == 0) {                                      // no rows: y = 0
+        SPMV_CUDA(cudaMemsetAsync(d_y, 0, (size_t)p->N * sizeof(float), st));
+        return SPMV_OK;
+    }
     const DevPanel &d = p->panel;
     if (d.index_bits == 8) return d.tiled ? launch_variant<8, true>(p, d_x, d_y, st) : launch_variant<8, false>(p, d_x, d_y, st);
     return d.tiled ? launch_variant<16, true>(p, d_x, d_y, st) : launch_variant<16, false>(p, d_x, d_y, st);
 }
 
-// Geometry: grid = (slabs, row splits).  A warp should own at least two 32-row blocks (so
-// the metadata prefetch has something to overlap), the grid should cover the SMs about
-// twice, and a CTA should stream clearly more than it spends zeroing / summing its
-// accumulator rows (kPanelWarps * slab_cols floats).
+// Geometry: a 1-D grid of G CTAs over the flat (slab, row) sequence, one resident wave.
+// Every CTA pays a few microseconds of serial latency (metadata, first chunks, cross-warp and
+// cross-piece sums), so more than one wave only adds latency (measured, profiles/r01_notes.md);
+// 8-warp CTAs, as many per SM as shared memory allows (at most 4: ~24-32 warps per SM).
 int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o)
 {
     DevPanel &d = p->panel;
     d.slab_cols = h.slab_cols; d.index_bits = h.index_bits; d.slabs = h.slabs;
     d.row_blocks = h.row_blocks; d.tiled = h.tiled;
-    // Geometry.  Every CTA pays a few microseconds of serial latency (metadata, first chunks,
-    // cross-warp and cross-split sums), so the grid is kept to one resident wave and the search
-    // below maximises how evenly that wave loads the SMs, the row blocks and the warps, at about
-    // 24 warps per SM in total (measured on B200, profiles/r01_notes.md).
-    const int rb = std::max(1, h.row_blocks);
-    const int slabs = std::max(1, h.slabs);
     const int smem_cap = p->max_smem_optin > 0 ? p->max_smem_optin : 227 * 1024;
     const int per_warp = h.index_bits == 8 ? warp_smem_bytes<8>(h.slab_cols) : warp_smem_bytes<16>(h.slab_cols);
-    int warps = 0, splits = 0;
-    double best = -1.0;
-    for (int w : {4, 8}) {
-        if (o && o->warps_per_col > 0 && w != std::min(kPanelMaxWarps, std::max(1, o->warps_per_col))) continue;
-        if (w * per_warp > smem_cap) continue;
-        const int resident = std::max(1, std::min(2048 / (w * 32), (228 * 1024) / (w * per_warp + 1024)));
-        for (int s0 = 1; s0 <= rb; s0++) {
-            if (o && o->row_splits > 0 && s0 != std::min(o->row_splits, rb)) continue;
-            const int bps = (rb + s0 - 1) / s0, s1 = (rb + bps - 1) / bps;
-            if (s1 != s0) continue;                                   // canonical split counts only
-            const int64_t ctas = (int64_t)slabs * s1;
-            const double per_sm = (double)ctas / p->sm_count;
-            const double sm_bal = per_sm / std::ceil(per_sm);                       // SMs equally loaded
-            const double row_bal = (double)rb / ((double)bps * s1);                  // splits equally long
-            const double warp_bal = (double)bps / (std::ceil((double)bps / w) * w);  // warps equally loaded
-            const double tw = (double)ctas * w / p->sm_count;                        // warps per SM
-            const double fill = std::min(1.0, tw / 24.0);
-            const double waves = (double)ctas / ((double)p->sm_count * resident);
-            const double wave_pen = waves <= 1.0 ? 1.0 : 1.0 / (0.6 + 0.4 * std::ceil(waves));
-            const double latency_pen = 1.0 / (1.0 + 0.02 * std::max(0.0, tw - 24.0));
-            const double score = sm_bal * row_bal * warp_bal * fill * wave_pen * latency_pen;
-            if (score > best + 1e-9) { best = score; warps = w; splits = s1; }
-        }
+    int warps = 8;
+    if (o && o->warps_per_col > 0) {
+        warps = 1;
+        while (warps * 2 <= std::min(kPanelMaxWarps, o->warps_per_col)) warps *= 2;   // power of two
     }
-    if (warps == 0) {                                                 // forced options outside the search space
-        warps = (o && o->warps_per_col > 0) ? std::min(kPanelMaxWarps, std::max(1, o->warps_per_col)) : 4;
-        splits = (o && o->row_splits > 0) ? std::min(o->row_splits, rb) : 1;
-        if (warps * per_warp > smem_cap)
-            return set_error(SPMV_ERR_UNSUPPORTED, "panel: %d bytes of shared memory exceed the device limit", warps * per_warp);
-    }
+    while (warps > 1 && warps * per_warp > smem_cap) warps /= 2;
+    if (warps * per_warp > smem_cap)
+        return set_error(SPMV_ERR_UNSUPPORTED, "panel: %d bytes of shared memory exceed the device limit", warps * per_warp);
     d.warps = warps;
     p->block = warps * 32;
     p->smem = warps * per_warp;
     p->tile_width = h.slab_cols;
     p->col_tiles = h.slabs;
     p->kernels_per_run = 1;
-    d.blocks_per_split = (rb + splits - 1) / splits;
-    splits = (rb + d.blocks_per_split - 1) / d.blocks_per_split;      // no empty splits
-    p->row_splits = splits;
-    p->grid = dim3((unsigned)slabs, (unsigned)splits, 1);
-    return alloc_split_scratch(p);
+
+    const int slabs = std::max(1, h.slabs);
+    const int64_t M = std::max<int64_t>(1, h.M);
+    const int resident = std::max(1, std::min(std::min(4, 2048 / p->block), (228 * 1024) / (p->smem + 1024)));
+    int64_t G = (int64_t)p->sm_count * resident;
+    if (o && o->row_splits > 0) G = (int64_t)slabs * o->row_splits;       // forced: row_splits CTAs per slab
+    const int64_t T = (int64_t)slabs * M;
+    G = std::max<int64_t>(1, std::min<int64_t>(G, (T + 31) / 32));         // at least 32 rows per CTA
+    const int64_t max_range = (T + G - 1) / G;
+    d.kmax = (int)(2 + max_range / M);
+    p->row_splits = (int)((G + slabs - 1) / slabs);                        // reported: CTAs per slab (rounded up)
+    p->grid = dim3((unsigned)G, 1, 1);
+    // scratch: one partial row per (CTA, piece) + one ticket per slab
+    p->partial = nullptr; p->tickets = nullptr;
+    return alloc_panel_scratch(p, (size_t)G * d.kmax * h.slab_cols, (size_t)slabs);
 }
 
 } // namespace spmv

@@ -55,7 +55,7 @@ struct DevPanel {
     int index_bits = 8;
     int slabs = 0, row_blocks = 0;
     int warps = 8;
-    int blocks_per_split = 0;   // row blocks (of 32 rows) per CTA
+    int kmax = 2;               // partial rows reserved per CTA (pieces of its flat range)
     bool tiled = false;
 };
 
@@ -117,4 +117,5 @@ int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o);
 void destroy_wsp_state(spmv_plan *p);
 int clone_wsp_state(const spmv_plan *src, spmv_plan *dst);
 int alloc_split_scratch(spmv_plan *p);   // partial + tickets from row_splits/col_tiles/tile_width
+int alloc_panel_scratch(spmv_plan *p, size_t partial_floats, size_t tickets);
 } // namespace spmv

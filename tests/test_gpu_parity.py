@@ -278,3 +278,30 @@ def test_traffic_accounting(S):
         with S.Plan.from_dense(v, A) as p:
             alg, phys, t = p.traffic(x)
             assert t == nnz_t and alg == 8 * nnz_t + 4 * 513 + vec
+
+
+def test_dropin_harness_binary(S):
+    """build/sparse_sgemv = test/main.cpp + the drop-in tester over the C-ABI (reference
+    test/main.cpp:1-7, tester.cpp:15-34): ten launchers on 4096x4096, every output inside the
+    reference's own abs-1e-3 gate."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "sparse_sgemv")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", root, "harness"])
+    env = dict(os.environ, SPMV_SEED="1234", SPMV_STRICT="1")
+    out = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "========== OK ===========" in out.stdout
+    assert out.stdout.count(" took ") == 10 and out.stdout.count("start to launch") == 10
+    assert out.stderr.strip() == ""
+
+
+def test_smoke_entry(S):
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import __graft_entry__ as g
+    g.smoke()
