@@ -67,11 +67,12 @@ typedef enum spmv_variant {
 /* Tuning knobs; zero-initialise for defaults.  struct_size must be sizeof(spmv_options_t). */
 typedef struct spmv_options {
     uint32_t struct_size;
-    int32_t  row_splits;     /* asp/awsp/tcsr: CTAs along M per column tile (0 = auto)   */
-    int32_t  warps_per_col;  /* wsp: warps cooperating on one column, 1/2/4/8 (0 = auto) */
+    int32_t  row_splits;     /* asp: CTAs along M per column tile; awsp/tcsr: CTAs per slab (0 = auto) */
+    int32_t  warps_per_col;  /* wsp: warps cooperating on one column, 1/2/4/8; awsp/tcsr: warps per CTA (0 = auto) */
     int32_t  index_bits;     /* wsp: 16 or 32 bit row indices (0 = auto: 16 if M<65536)  */
     int32_t  slab_cols;      /* awsp/tcsr: columns per slab, power of two 256..4096 (0 = auto from density) */
-    int32_t  reserved[3];
+    int32_t  chunk_mode;     /* awsp/tcsr: 0 = auto, 1 = one row per 32-group chunk, 2 = short rows packed into shared chunks */
+    int32_t  reserved[2];
 } spmv_options_t;
 
 typedef struct spmv_plan spmv_plan_t;   /* opaque */

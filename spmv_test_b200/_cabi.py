@@ -29,7 +29,8 @@ class SpmvError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("row_splits", C.c_int32), ("warps_per_col", C.c_int32),
-                ("index_bits", C.c_int32), ("slab_cols", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("index_bits", C.c_int32), ("slab_cols", C.c_int32), ("chunk_mode", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
 
 
 class PlanInfo(C.Structure):

@@ -156,6 +156,7 @@ static bool opts_ok(const spmv_options_t *o)
     if (o->struct_size != sizeof(spmv_options_t)) return false;
     if (o->row_splits < 0 || o->warps_per_col < 0) return false;
     if (o->index_bits != 0 && o->index_bits != 16 && o->index_bits != 32) return false;
+    if (o->chunk_mode < 0 || o->chunk_mode > 2) return false;
     if (o->slab_cols != 0 && (o->slab_cols < kMinSlabCols || o->slab_cols > kMaxSlabCols || (o->slab_cols & (o->slab_cols - 1))))
         return false;
     return true;

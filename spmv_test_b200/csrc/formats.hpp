@@ -46,7 +46,7 @@ constexpr int kMinSlabCols = 256;
 constexpr int kMaxSlabCols = 4096;
 
 struct HostPanel {
-    int64_t M = 0, N = 0, nnz = 0, groups = 0;
+    int64_t M = 0, N = 0, nnz = 0, groups = 0, nonempty_segments = 0;
     int slab_cols = 256;
     int index_bits = 8;          // 8 when slab_cols == 256, else 16
     int slabs = 0;

@@ -208,7 +208,7 @@ int pack_panel(int64_t M, int64_t N, bool tiled, int W, Source &src, HostPanel &
     P.row_nnz.assign((size_t)M, 0);
     P.row_groups.assign((size_t)M, 0);
     P.row_segs.assign((size_t)M, 0);
-    P.nnz = 0; P.groups = 0;
+    P.nnz = 0; P.groups = 0; P.nonempty_segments = 0;
     P.vals.clear(); P.idx8.clear(); P.idx16.clear(); P.rel.clear();
     const int64_t per_slab = tiled ? (P.row_blocks + 1) : (M + 1);
     P.off.assign((size_t)P.slabs * per_slab, 0);
@@ -281,7 +281,7 @@ int pack_panel(int64_t M, int64_t N, bool tiled, int W, Source &src, HostPanel &
                 const int n = src.get(s, row, cols.data(), vals.data());
                 if (n) {
                     const int g = emit(n);
-                    P.row_nnz[row] += n; P.row_groups[row] += g; P.row_segs[row] += 1; P.nnz += n;
+                    P.row_nnz[row] += n; P.row_groups[row] += g; P.row_segs[row] += 1; P.nnz += n; P.nonempty_segments++;
                 }
             }
             if (P.groups - tile_first > 65535) return SPMV_ERR_UNSUPPORTED;   // u16 rel offsets
@@ -304,6 +304,10 @@ int choose_slab_cols(int64_t M, int64_t N, int64_t nnz)
     const double density = (double)nnz / ((double)M * (double)N);
     int w = kMinSlabCols;
     while (w < kMaxSlabCols && w * density < 300.0) w <<= 1;
+    // very sparse: segments stay short whatever the width and the kernel packs several rows per
+    // chunk anyway; 2048 columns keep the accumulator rows small enough for 8 warps and a
+    // 16-deep ring per SM
+    if (w == kMaxSlabCols && w * density < 80.0) w = 2048;
     const int64_t row_blocks = (M + kTileRows - 1) / kTileRows;
     while (w > kMinSlabCols && ((N + w - 1) / w) * row_blocks < 1024) w >>= 1;
     return w;

@@ -31,7 +31,8 @@ namespace {
 
 constexpr int kPanelMaxWarps = 8;
 constexpr int kPanelThreads = kPanelMaxWarps * 32;   // launch bound; the CTA size is a plan parameter
-constexpr int kStages = 8;                   // chunks in flight per warp (cp.async groups)
+// chunks in flight per warp (cp.async groups): 8 in single-row mode, 16 in multi-row mode,
+// where accumulator rows leave room for fewer warps and the ring has to carry the latency
 
 template <int IDXB> struct ColIdx;
 template <> struct ColIdx<8> {
@@ -59,12 +60,14 @@ template <> struct ColIdx<16> {
     static __device__ __forceinline__ Vec zero() { return make_uint2(0u, 0u); }
 };
 
-// per-warp shared memory: [acc: W floats][vals ring: kStages x 32 float4][idx ring][list: 64 x uint4][slot info]
+// per-warp shared memory: [acc: W floats][vals ring: kStages x 32 float4][idx ring][list: 128 x uint4]
+//                         [slot info][multi-row mode: per-lane (x, row slot) ring]
 constexpr int kListCap = 128;              // rows a warp can take from one metadata batch
+constexpr int kStreamMinActive = 11;       // active rows (of 32) from which a block is streamed whole
 constexpr int kMetaBatch = 4;              // 32-row blocks of metadata fetched together
-template <int IDXB> __host__ __device__ constexpr int warp_smem_bytes(int W)
+template <int IDXB, int kStages> __host__ __device__ constexpr int warp_smem_bytes(int W)
 {
-    return W * 4 + kStages * 32 * 16 + kStages * 32 * (IDXB == 8 ? 4 : 8) + kListCap * 16 + kStages * 8;
+    return W * 4 + kStages * 32 * 16 + kStages * 32 * (IDXB == 8 ? 4 : 8) + kListCap * 16 + kStages * 8 + kStages * 32 * 8;
 }
 
 // Balanced flat decomposition.  The (slab, row) pairs, slab-major, form one sequence of
@@ -77,7 +80,7 @@ template <int IDXB> __host__ __device__ constexpr int warp_smem_bytes(int W)
 __device__ __forceinline__ long long range_begin(long long c, long long T, long long G) { return c * T / G; }
 __device__ __forceinline__ long long cta_of_unit(long long u, long long T, long long G) { return ((u + 1) * G - 1) / T; }
 
-template <int IDXB, bool TILED>
+template <int IDXB, bool TILED, bool MR, int kStages>
 __global__ void __launch_bounds__(kPanelThreads)
 panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
              const uint32_t *__restrict__ off, const uint16_t *__restrict__ rel,
@@ -92,12 +95,13 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_warps = blockDim.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes<IDXB>(W);
+    unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes<IDXB, kStages>(W);
     float *acc = reinterpret_cast<float *>(wbase);
     float4 *ring_v = reinterpret_cast<float4 *>(wbase + (size_t)W * 4);
     IVec *ring_i = reinterpret_cast<IVec *>(wbase + (size_t)W * 4 + kStages * 32 * 16);
     uint4 *list = reinterpret_cast<uint4 *>(wbase + (size_t)W * 4 + kStages * 32 * 16 + kStages * 32 * sizeof(IVec));
-    uint2 *sinfo = reinterpret_cast<uint2 *>(list + kListCap);   // per ring slot: (valid lanes, x of the row)
+    uint2 *sinfo = reinterpret_cast<uint2 *>(list + kListCap);   // per ring slot: (valid lanes, x of the row | passes)
+    uint2 *ring_m = sinfo + kStages;                             // MR: per lane (x of its row, row slot in the chunk)
     const int wg = blockIdx.x * n_warps + warp;           // trace id
     (void)wg;
     SPMV_STAMP(wg, 0);
@@ -165,6 +169,63 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         }
     };
 
+    // Multi-row mode (short segments, e.g. 1 % density): a chunk is 32 consecutive groups of the
+    // warp's active rows laid end to end, so every cp.async moves 32 full lanes however short
+    // the rows are.  Rows of one chunk may share columns, so the chunk is retired in passes, one
+    // row (slot) at a time, in ascending row order.
+    auto retire_mr = [&](int s) {
+        const uint2 info = sinfo[s];                      // (valid lanes, passes)
+        const float4 a = ring_v[s * 32 + lane];
+        uint32_t c[4];
+        CI::unpack(ring_i[s * 32 + lane], c);
+        const uint2 mine = ring_m[s * 32 + lane];         // written by this lane at issue time
+        const float p = __uint_as_float(mine.x);
+        const bool live = lane < info.x;
+        for (uint32_t pass = 0; pass < info.y; pass++) {
+            if (live && mine.y == pass && p != 0.0f) {
+                float r0 = acc[c[0]], r1 = acc[c[1]], r2 = acc[c[2]], r3 = acc[c[3]];
+                r0 = fmaf(a.x, p, r0); r1 = fmaf(a.y, p, r1); r2 = fmaf(a.z, p, r2); r3 = fmaf(a.w, p, r3);
+                acc[c[0]] = r0; acc[c[1]] = r1; acc[c[2]] = r2; acc[c[3]] = r3;
+            }
+            __syncwarp();
+        }
+    };
+    auto run_list_mr = [&](int n_rows) {
+        for (int base = 0; base < n_rows; base += 32) {   // lane i <-> row base + i of the list
+            const uint4 m = base + lane < n_rows ? list[base + lane] : make_uint4(0u, 0u, 0u, 0u);
+            const int cgr = (int)(m.y - m.x);             // groups of this lane's row (>= 1 when present)
+            const int pend = warp_incl_scan(cgr, lane);   // flat position one past the row's last group
+            const int pbeg = pend - cgr;
+            const int total = __shfl_sync(kFull, pend, 31);
+#pragma unroll 1
+            for (int k0 = 0; k0 < total; k0 += 32) {
+                const int s = it++ & (kStages - 1);
+                cp_async_wait<kStages - 1>();
+                retire_mr(s);
+                // which row does flat position k0 + lane belong to?  rows ending inside the chunk
+                // set one bit each; rows that ended before it are counted by a ballot
+                const unsigned e = (unsigned)(pend - k0 - 1);
+                const unsigned endbit = (cgr > 0 && e < 32u) ? (1u << e) : 0u;
+                const unsigned ends = __reduce_or_sync(kFull, endbit);
+                // passes are numbered over the rows that take part in the arithmetic (x != 0)
+                const unsigned ends_act = __reduce_or_sync(kFull, __uint_as_float(m.z) != 0.0f ? endbit : 0u);
+                const int i_first = __popc(__ballot_sync(kFull, cgr > 0 && pend <= k0));
+                const int q = k0 + lane;
+                const bool ok = q < total;
+                const int i = min(31, i_first + __popc(ends & lt));
+                const uint32_t g0_i = __shfl_sync(kFull, m.x, i);
+                const int pb_i = __shfl_sync(kFull, pbeg, i);
+                const uint32_t x_i = __shfl_sync(kFull, m.z, i);
+                const uint32_t gs = ok ? g0_i + (uint32_t)(q - pb_i) : g0_i;
+                cp_async16_zfill(ring_v + s * 32 + lane, vals + gs, ok);
+                CI::copy(ring_i + s * 32 + lane, idx, gs, ok);
+                cp_async_commit();
+                ring_m[s * 32 + lane] = make_uint2(x_i, (uint32_t)__popc(ends_act & lt));
+                const int n_lanes = min(32, total - k0);
+                if (lane == 0) sinfo[s] = make_uint2((uint32_t)n_lanes, (uint32_t)__popc(ends_act) + 1u);
+            }
+        }
+    };
     int piece = 0;
     for (long long u = u_begin; u < u_end; piece++) {
         const int slab = (int)(u / M);
@@ -183,42 +244,58 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         // a CTA end up with equal shares whatever the piece length.
         // Metadata is fetched kMetaBatch blocks at a time, one batch ahead of its use, so its
         // latency is paid once per 128 rows and overlaps the previous batch's streaming.
+        // Long pieces: warp w owns blocks w, w + n_warps, ... outright (no redundant metadata
+        // loads, statistically balanced).  Short pieces: every warp scans every block and keeps
+        // the active rows whose rank is w modulo the warp count (exact balance).
         const int blk_a = row_a >> 5, blk_b = (row_b + 31) >> 5;
+        const bool by_block = (blk_b - blk_a) >= 4 * n_warps;
+        const int bstep = by_block ? n_warps : 1;
+        const int bfirst = blk_a + (by_block ? warp : 0);
         int rank_base = 0;
         Meta nxt[kMetaBatch];
 #pragma unroll
         for (int j = 0; j < kMetaBatch; j++)
-            if (blk_a + j < blk_b) nxt[j] = load_meta(slab, blk_a + j);
-        for (int blk0 = blk_a; blk0 < blk_b; blk0 += kMetaBatch) {
+            if (bfirst + j * bstep < blk_b) nxt[j] = load_meta(slab, bfirst + j * bstep);
+        for (int blk0 = bfirst; blk0 < blk_b; blk0 += kMetaBatch * bstep) {
             Meta cur[kMetaBatch];
 #pragma unroll
             for (int j = 0; j < kMetaBatch; j++) cur[j] = nxt[j];
 #pragma unroll
             for (int j = 0; j < kMetaBatch; j++)
-                if (blk0 + kMetaBatch + j < blk_b) nxt[j] = load_meta(slab, blk0 + kMetaBatch + j);
+                if (blk0 + (kMetaBatch + j) * bstep < blk_b) nxt[j] = load_meta(slab, blk0 + (kMetaBatch + j) * bstep);
             int cnt = 0;
 #pragma unroll
             for (int j = 0; j < kMetaBatch; j++) {
-                const int row = (blk0 + j) * 32 + lane;
-                const bool valid = blk0 + j < blk_b && row >= row_a && row < row_b && cur[j].xv != 0.0f && cur[j].g1 > cur[j].g0;
+                const int blk = blk0 + j * bstep;
+                const int row = blk * 32 + lane;
+                const bool nonempty = blk < blk_b && row >= row_a && row < row_b && cur[j].g1 > cur[j].g0;
+                const bool active = nonempty && cur[j].xv != 0.0f;
+                // Short segments with many active rows (multi-row mode, block owned outright):
+                // fetching only the active rows would read scattered ~100-byte pieces, which
+                // DRAM serves at a fraction of its bandwidth (measured), so the whole block is
+                // streamed contiguously and the inactive rows are skipped in the arithmetic only.
+                const bool stream = MR && by_block && __popc(__ballot_sync(kFull, active)) >= kStreamMinActive;
+                const bool valid = stream ? nonempty : active;
                 const unsigned mask = __ballot_sync(kFull, valid);
                 const int rank = rank_base + __popc(mask & lt);
-                const bool mine = valid && (rank & (n_warps - 1)) == warp;   // n_warps is a power of two
+                const bool mine = valid && (by_block || (rank & (n_warps - 1)) == warp);   // n_warps is a power of two
                 const unsigned mm = __ballot_sync(kFull, mine);
                 if (mine) list[cnt + __popc(mm & lt)] = make_uint4(cur[j].g0, cur[j].g1, __float_as_uint(cur[j].xv), 0u);
                 cnt += __popc(mm);
                 rank_base += __popc(mask);
             }
             __syncwarp();
-            if (piece == 0 && blk0 == blk_a) SPMV_STAMP(wg, 1);
-            run_list(cnt);
+            if (piece == 0 && blk0 == bfirst) SPMV_STAMP(wg, 1);
+            if (MR) run_list_mr(cnt); else run_list(cnt);
             __syncwarp();                                 // the list is rewritten next
         }
         SPMV_STAMP(wg, 2);
         cp_async_wait<0>();
         SPMV_STAMP(wg, 3);
 #pragma unroll 1
-        for (int k = 0; k < kStages; k++) retire(it++ & (kStages - 1));
+        for (int k = 0; k < kStages; k++) {
+            if (MR) retire_mr(it++ & (kStages - 1)); else retire(it++ & (kStages - 1));
+        }
         SPMV_STAMP(wg, 4);
 
         // ---- fixed-order sum over warps, then over the slab's pieces -----------------------------
@@ -229,7 +306,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         const int n_pieces = (int)(c_hi - c_lo + 1);
         const int col0 = slab * W;
         const int n_valid = min(W, N - col0);
-        const int wstride = warp_smem_bytes<IDXB>(W) / 4;
+        const int wstride = warp_smem_bytes<IDXB, kStages>(W) / 4;
         const float *acc0 = reinterpret_cast<const float *>(smem_raw);
         float *dst = n_pieces == 1 ? y + col0 : partial + ((size_t)blockIdx.x * kmax + piece) * W;
         for (int c = tid; c < n_valid; c += blockDim.x) {
@@ -257,10 +334,10 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     }
 }
 
-template <int IDXB, bool TILED>
+template <int IDXB, bool TILED, bool MR>
 int launch_variant(spmv_plan *p, const float *x, float *y, cudaStream_t st)
 {
-    auto k = panel_kernel<IDXB, TILED>;
+    auto k = panel_kernel<IDXB, TILED, MR, MR ? 16 : 8>;
     if (p->smem > 48 * 1024)
         SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem));
     const DevPanel &d = p->panel;
@@ -281,8 +358,12 @@ int launch_panel(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st)
         return SPMV_OK;
     }
     const DevPanel &d = p->panel;
-    if (d.index_bits == 8) return d.tiled ? launch_variant<8, true>(p, d_x, d_y, st) : launch_variant<8, false>(p, d_x, d_y, st);
-    return d.tiled ? launch_variant<16, true>(p, d_x, d_y, st) : launch_variant<16, false>(p, d_x, d_y, st);
+    if (d.multirow) {
+        if (d.index_bits == 8) return d.tiled ? launch_variant<8, true, true>(p, d_x, d_y, st) : launch_variant<8, false, true>(p, d_x, d_y, st);
+        return d.tiled ? launch_variant<16, true, true>(p, d_x, d_y, st) : launch_variant<16, false, true>(p, d_x, d_y, st);
+    }
+    if (d.index_bits == 8) return d.tiled ? launch_variant<8, true, false>(p, d_x, d_y, st) : launch_variant<8, false, false>(p, d_x, d_y, st);
+    return d.tiled ? launch_variant<16, true, false>(p, d_x, d_y, st) : launch_variant<16, false, false>(p, d_x, d_y, st);
 }
 
 // Geometry: a 1-D grid of G CTAs over the flat (slab, row) sequence, one resident wave.
@@ -294,8 +375,14 @@ int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o)
     DevPanel &d = p->panel;
     d.slab_cols = h.slab_cols; d.index_bits = h.index_bits; d.slabs = h.slabs;
     d.row_blocks = h.row_blocks; d.tiled = h.tiled;
+    // short segments (fewer than ~20 groups on average): pack several rows into one chunk
+    const double segs = std::max<double>(1.0, (double)h.nonempty_segments);
+    d.multirow = (double)h.groups / segs < 20.0;
+    if (o && o->chunk_mode == 1) d.multirow = false;
+    if (o && o->chunk_mode == 2) d.multirow = true;
     const int smem_cap = p->max_smem_optin > 0 ? p->max_smem_optin : 227 * 1024;
-    const int per_warp = h.index_bits == 8 ? warp_smem_bytes<8>(h.slab_cols) : warp_smem_bytes<16>(h.slab_cols);
+    const int per_warp = d.multirow ? (h.index_bits == 8 ? warp_smem_bytes<8, 16>(h.slab_cols) : warp_smem_bytes<16, 16>(h.slab_cols))
+                                    : (h.index_bits == 8 ? warp_smem_bytes<8, 8>(h.slab_cols) : warp_smem_bytes<16, 8>(h.slab_cols));
     int warps = 8;
     if (o && o->warps_per_col > 0) {
         warps = 1;

@@ -57,6 +57,7 @@ struct DevPanel {
     int warps = 8;
     int kmax = 2;               // partial rows reserved per CTA (pieces of its flat range)
     bool tiled = false;
+    bool multirow = false;      // several short rows per 32-group chunk
 };
 
 } // namespace spmv

@@ -146,7 +146,8 @@ def test_column_slab_view_with_lda(S):
 
 @pytest.mark.parametrize("opts", [dict(row_splits=1), dict(row_splits=3), dict(row_splits=64),
                                   dict(slab_cols=512), dict(slab_cols=4096), dict(index_bits=32),
-                                  dict(warps_per_col=1), dict(warps_per_col=8)])
+                                  dict(warps_per_col=1), dict(warps_per_col=8), dict(chunk_mode=1), dict(chunk_mode=2),
+                                  dict(chunk_mode=2, slab_cols=256, row_splits=5), dict(chunk_mode=2, warps_per_col=2)])
 def test_options(S, opts):
     A = ob.gen_matrix(2048, 1024, 0.8, 11)
     x = ob.gen_vector(2048, 0.5, 12)
@@ -225,11 +226,16 @@ def test_config5_sharded_slab_scaled(S):
     y_ref = ob.csc_gemv(N, ptr, idx, val, x)
     s = ob.csc_gemv(N, ptr, idx, np.abs(val), np.abs(x)).astype(np.float64)
     for v in ("awsp", "tcsr", "wsp"):
-        with S.Plan.from_csc(v, M, N, ptr, idx, val) as p:
-            if v != "wsp":
-                assert p.info()["slab_cols"] > 256
-            err = np.abs(p.run_host(x).astype(np.float64) - y_ref)
-            assert float(np.max(err / (s + 1e-30))) <= 1e-5, v
+        for opts in ({}, dict(chunk_mode=1), dict(chunk_mode=2, row_splits=2), dict(chunk_mode=2, warps_per_col=4)):
+            if v == "wsp" and opts:
+                continue
+            with S.Plan.from_csc(v, M, N, ptr, idx, val, **opts) as p:
+                if v != "wsp":
+                    assert p.info()["slab_cols"] > 256
+                y = p.run_host(x)
+                err = np.abs(y.astype(np.float64) - y_ref)
+                assert float(np.max(err / (s + 1e-30))) <= 1e-5, (v, opts)
+                assert p.run_host(x).tobytes() == y.tobytes(), "non-deterministic"
 
 
 @pytest.mark.parametrize("M,sx", [(1, 0.0), (31, 0.5), (4096, 0.5), (14336, 0.9), (32768, 0.5),
