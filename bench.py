@@ -5,9 +5,10 @@
     python bench.py --impl reference ...                    (the reference's CPU path, rank 0)
 
 N = 1   workload = BASELINE config 2 (LLM decode FFN up-proj: A 4096x14336, 70 % weight-sparse,
-        x 50 % activation-sparse).  A step is one call of the headline variant (awsp); the other
-        variants (wsp, asp, tcsr) and the other single-GPU configs are timed the same way in the
-        same run and reported under "variants" / "configs".
+        x 50 % activation-sparse).  The config names three variants (wsp; asp/awsp), so a step is
+        one call of each of them on the same A and x; every variant (and tcsr, and the other
+        single-GPU configs) is also timed alone and reported under "variants" / "configs", and
+        "roofline" describes the step's dominant (longest) kernel.
 N > 1   workload = BASELINE config 5 family, weak scaling: every rank owns a 131072-column slab
         of A (65536 rows, 99 % sparse, built directly in sparse form), x is replicated, a step is
         the local awsp call plus the NCCL all-gather of Y.  At N = 8 this is exactly config 5
@@ -38,7 +39,8 @@ sys.path.insert(0, ROOT)
 METRIC = "sparse SGEMV Y=xA effective HBM throughput (algorithmic bytes / device time)"
 UNIT = "GB/s"
 L2_BYTES = 126e6
-HEADLINE = "awsp"
+HEADLINE = "awsp"                      # multi-GPU (config 5) variant
+STEP_VARIANTS = ("wsp", "asp", "awsp")   # config 2 names all three: one step = one call of each
 C5_M, C5_SLAB_N, C5_DENSITY, C5_SX = 65536, 131072, 0.01, 0.5
 
 
@@ -107,26 +109,60 @@ def make_copies(plan, want_bytes=2.5 * L2_BYTES, max_copies=12):
     return [plan] + [plan.clone() for _ in range(n - 1)]
 
 
-def time_loop(torch, plans, dx, dy, steps, warmup, stream, after=None):
-    """Device time (ms) of `steps` calls rotating over `plans`, CUDA events on `stream`."""
+GRAPH_STEPS = 100   # steps captured per CUDA graph
+GRAPH = True        # --no-graph clears it
+
+
+def timed_steps(torch, step, steps, warmup, stream, graph=True):
+    """Device time (ms) of exactly `steps` calls of step(i, cuda_stream) on `stream`, CUDA events,
+    device-wide synchronize on both sides.  With graph=True the steps are captured into CUDA
+    graphs (GRAPH_STEPS per graph, replayed back to back; a second graph for the remainder):
+    kernels launched one by one into a stream start on a ~2 us dispatch cadence on this driver,
+    a graph runs them back to back (tools/graph_vs_stream.py: 2.0-2.6 us per call)."""
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = len(plans)
     with torch.cuda.stream(stream):
         for i in range(warmup):
-            plans[i % n].run(dx, dy, stream.cuda_stream)
-            if after:
-                after()
+            step(i, stream.cuda_stream)
+        stream.synchronize()
+        if not graph:
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for i in range(steps):
+                step(i, stream.cuda_stream)
+            e1.record(stream)
+            stream.synchronize()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1)
+        per = min(GRAPH_STEPS, steps)
+        reps, rem = divmod(steps, per)
+        graphs = []
+        for n in ([per] if rem == 0 else [per, rem]):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                cs = torch.cuda.current_stream().cuda_stream
+                for i in range(n):
+                    step(i, cs)
+            graphs.append(g)
+        graphs[0].replay()                                 # untimed: first replay uploads the graph
+        if rem:
+            graphs[1].replay()
         stream.synchronize()
         torch.cuda.synchronize()
         e0.record(stream)
-        for i in range(steps):
-            plans[i % n].run(dx, dy, stream.cuda_stream)
-            if after:
-                after()
+        for _ in range(reps):
+            graphs[0].replay()
+        if rem:
+            graphs[1].replay()
         e1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
     return e0.elapsed_time(e1)
+
+
+def time_loop(torch, plans, dx, dy, steps, warmup, stream, graph=True):
+    """`steps` calls rotating over `plans` (clones of one matrix, > 2.5x L2 in total)."""
+    n = len(plans)
+    return timed_steps(torch, lambda i, cs: plans[i % n].run(dx, dy, cs), steps, warmup, stream, graph)
 
 
 def measure_variant(torch, S, variant, build, x, steps, warmup, stream, check=None):
@@ -143,7 +179,7 @@ def measure_variant(torch, S, variant, build, x, steps, warmup, stream, check=No
         plan.run(dx, dy, stream.cuda_stream)
         stream.synchronize()
         check(variant, dy.cpu().numpy())
-    ms = time_loop(torch, plans, dx, dy, steps, warmup, stream)
+    ms = time_loop(torch, plans, dx, dy, steps, warmup, stream, graph=GRAPH)
     us = ms * 1e3 / steps
     res = {"us_per_call": round(us, 3), "alg_MB": round(alg / 1e6, 3), "phys_MB": round(phys / 1e6, 3),
            "eff_GBps": round(alg / (us * 1e-6) / 1e9, 1), "phys_GBps": round(phys / (us * 1e-6) / 1e9, 1),
@@ -168,11 +204,25 @@ def e2e_loop(plan, x, N, steps, warmup, torch):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_sampled(A, x, alg_bytes, steps, warmup, budget_s=100.0):
+def step_alg_bytes(A, x, names):
+    """Algorithmic bytes of one step = one call of each variant in `names`."""
+    M, N = A.shape
+    nnz = int(np.count_nonzero(A))
+    act = x != 0
+    nnz_t = int(np.count_nonzero(A[act]))
+    mnz = int(np.count_nonzero(act))
+    vec = 4.0 * M + 4.0 * N
+    per = {"wsp": 8.0 * nnz + 4 * (N + 1) + vec, "tcsr": 8.0 * nnz_t + 4 * (N + 1) + vec,
+           "awsp": 8.0 * nnz_t + 4 * (N + 1) + vec, "asp": 4.0 * mnz * N + vec}
+    return sum(per[v] for v in names)
+
+
+def cpu_reference_sampled(A, x, alg_bytes, steps, warmup, calls_per_step=1, budget_s=100.0):
     """The reference's own CPU path (SgemvCPU, tester.cpp:36-45) from oracle/_ref when it was
-    built, else the oracle's restatement of it.  One step = one call on the first `rows` rows of
-    the full-width matrix (row stride stays N, as in the reference), `rows` chosen so the run fits
-    the time budget; throughput is scaled by rows/M."""
+    built, else the oracle's restatement of it.  The reference has one CPU implementation for
+    every variant, so a step of `calls_per_step` SGEMV calls is that many SgemvCPU calls.  Each
+    call runs on the first `rows` rows of the full-width matrix (row stride stays N, as in the
+    reference), `rows` chosen so the run fits the time budget; throughput is scaled by rows/M."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_bindings as ob
     if ob.have_ref_cpu():
@@ -184,20 +234,21 @@ def cpu_reference_sampled(A, x, alg_bytes, steps, warmup, budget_s=100.0):
     t0 = time.perf_counter()
     fn(A[:probe_rows], x[:probe_rows])
     per_row = (time.perf_counter() - t0) / probe_rows
-    rows = int(min(M, max(32, budget_s / max(1, steps + warmup) / per_row)))
+    rows = int(min(M, max(32, budget_s / max(1, (steps + warmup) * calls_per_step) / per_row)))
     rows = max(32, rows // 32 * 32)
     Ar, xr = np.ascontiguousarray(A[:rows]), np.ascontiguousarray(x[:rows])
-    for _ in range(warmup):
+    for _ in range(warmup * calls_per_step):
         fn(Ar, xr)
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(steps * calls_per_step):
         fn(Ar, xr)
     dt = (time.perf_counter() - t0) / steps
     frac = rows / M
     gbps = alg_bytes * frac / dt / 1e9
-    sample = (f"{steps} calls of {'the reference SgemvCPU (tester.cpp:36-45, oracle/_ref)' if kind == 'reference' else 'the oracle port of SgemvCPU'}"
-              f" on the first {rows} of {M} rows of the full-width {M}x{N} matrix (dense loop, 1 thread, "
-              f"{dt * 1e3:.1f} ms per call; full-matrix call ~{dt / frac * 1e3:.0f} ms)")
+    what = "the reference SgemvCPU (tester.cpp:36-45, oracle/_ref)" if kind == "reference" else "the oracle port of SgemvCPU"
+    sample = (f"{steps} steps of {calls_per_step} call(s) of {what} on the first {rows} of {M} rows of the "
+              f"full-width {M}x{N} matrix (dense loop, 1 thread, {dt / calls_per_step * 1e3:.1f} ms per call; "
+              f"full-matrix call ~{dt / calls_per_step / frac * 1e3:.0f} ms)")
     return gbps, dt, kind, sample, frac
 
 
@@ -209,13 +260,13 @@ def run_reference_arm(args):
     M, N, sa, sx = synth.CONFIGS["c2"]
     A = synth.gen_matrix(M, N, sa)
     x = synth.gen_vector(M, sx)
-    nnz_t = int(np.count_nonzero(A[x != 0]))
-    alg = 8.0 * nnz_t + 4 * (N + 1) + 4 * M + 4 * N
-    gbps, dt, kind, sample, frac = cpu_reference_sampled(A, x, alg, args.steps, args.warmup)
+    names = list(STEP_VARIANTS)
+    alg = step_alg_bytes(A, x, names)
+    gbps, dt, kind, sample, frac = cpu_reference_sampled(A, x, alg, args.steps, args.warmup, calls_per_step=len(names))
     line = {"impl": "reference", "metric": METRIC, "value": round(gbps, 4), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config("c2", HEADLINE, None),
+            "config": workload_config("c2", "+".join(names), None),
             "cpu_baseline": {"value": round(gbps, 4), "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
             "e2e": {"value": round(gbps, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -224,8 +275,8 @@ def run_reference_arm(args):
 
 def workload_config(cfg, variant, l2):
     if cfg == "c2":
-        return {"workload": "BASELINE config 2: A 4096x14336 fp32, 70% weight-sparse, x 50% activation-sparse, "
-                            f"variant {variant} (activation+weight sparse), seeds 1234/4321",
+        return {"workload": "BASELINE config 2: A 4096x14336 fp32, 70% weight-sparse, x 50% activation-sparse; one step = "
+                            f"one SGEMV call of each variant in [{variant}] on the same A and x, seeds 1234/4321",
                 "M": 4096, "N": 14336, "weight_sparsity": 0.7, "activation_sparsity": 0.5, "variant": variant,
                 "l2": l2}
     return {"workload": "BASELINE config 5 family (weak scaling): per GPU a 131072-column slab of A "
@@ -255,6 +306,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--quick", action="store_true", help="headline variant only (used under ncu)")
     ap.add_argument("--no-aux", action="store_true", help="skip config 4 / config-5 slab / CPU baseline legs")
+    ap.add_argument("--no-graph", action="store_true", help="launch every call into the stream instead of replaying CUDA graphs")
     ap.add_argument("--variant", default=None, help="headline variant override (for profiling one kernel)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -262,9 +314,8 @@ def main():
         args.warmup = 3 if args.warmup is None else args.warmup
         run_reference_arm(args)
         return
-    global HEADLINE
-    if args.variant:
-        HEADLINE = args.variant
+    global GRAPH
+    GRAPH = not args.no_graph
     args.steps = 2000 if args.steps is None else args.steps
     args.warmup = 50 if args.warmup is None else max(3, args.warmup)
 
@@ -289,24 +340,46 @@ def main():
     extra = {}
 
     if world == 1:
-        # ---------------- single GPU: config 2, all variants ------------------------------------
+        # ---------------- single GPU: config 2, one step = wsp + asp + awsp -----------------------
         M, N, sa, sx = synth.CONFIGS["c2"]
         A = synth.gen_matrix(M, N, sa)
         x = synth.gen_vector(M, sx)
-        res, plans, (dx, dy), (alg, phys) = measure_variant(
-            torch, S, HEADLINE, lambda v: S.Plan.from_dense(v, A), x, args.steps, args.warmup, stream)
-        ms = res["us_per_call"] * args.steps / 1e3
-        value = alg / (res["us_per_call"] * 1e-6) / 1e9
-        y_dev = dy.cpu().numpy()
-        e2e_s, h2d, d2h, y_e2e = e2e_loop(plans[0], x, N, args.steps, args.warmup, torch)
-        assert y_e2e.tobytes() == y_dev.tobytes(), "host-buffer path and device path disagree"
-        launches = args.steps * plans[0].info()["kernels_per_run"]
-        variants = {HEADLINE: res}
-        l2 = f"rotation over {len(plans)} resident copies of the packed matrix ({res['resident_MB']} MB each) > 2.5x L2"
-        if not args.quick:
-            for p in plans[1:]:
+        names = [args.variant] if args.variant else list(STEP_VARIANTS)
+        variants, sets, algs, physs = {}, {}, {}, {}
+        for v in names:
+            res, plans, (dx, dy), (alg, phys) = measure_variant(
+                torch, S, v, lambda vv: S.Plan.from_dense(vv, A), x, args.steps, args.warmup, stream)
+            variants[v], sets[v], algs[v], physs[v] = res, plans, alg, phys
+        # the timed region: K steps, each one call of every variant the config names
+        def step(i, cs):
+            for v in names:
+                pl = sets[v]
+                pl[i % len(pl)].run(dx, dy, cs)
+        ms = timed_steps(torch, step, args.steps, args.warmup, stream, graph=not args.no_graph)
+        alg_step = sum(algs.values())
+        value = alg_step / (ms / args.steps * 1e-3) / 1e9
+        # end to end through the host-buffer C-ABI call (H2D x, kernels, D2H y, synchronise)
+        e2e_s, h2d, d2h = 0.0, 0, 0
+        for v in names:
+            plans = sets[v]
+            plans[0].run(dx, dy, stream.cuda_stream)
+            stream.synchronize()
+            y_dev = dy.cpu().numpy()
+            t, bi, bo, y_e2e = e2e_loop(plans[0], x, N, args.steps, args.warmup, torch)
+            assert y_e2e.tobytes() == y_dev.tobytes(), f"{v}: host-buffer path and device path disagree"
+            variants[v]["e2e_us_per_call"] = round(t * 1e6, 2)
+            e2e_s += t
+            h2d += bi
+            d2h += bo
+        launches = args.steps * sum(sets[v][0].info()["kernels_per_run"] for v in names)
+        l2 = ("rotation over resident copies of every packed matrix (" +
+              ", ".join(f"{v}: {len(sets[v])} x {variants[v]['resident_MB']} MB" for v in names) + "), each > 2.5x L2 in total")
+        dominant = max(names, key=lambda v: variants[v]["us_per_call"])
+        for v in names:
+            for p in sets[v][1:]:
                 p.close()
-            for v in [v for v in ("wsp", "asp", "awsp", "tcsr") if v != HEADLINE]:
+        if not args.quick:
+            for v in [v for v in ("wsp", "asp", "awsp", "tcsr") if v not in names]:
                 r, pl, _, _ = measure_variant(torch, S, v, lambda vv: S.Plan.from_dense(vv, A), x,
                                               args.steps, args.warmup, stream)
                 variants[v] = r
@@ -341,14 +414,19 @@ def main():
                     p.close()
             except Exception as e:  # never lose the headline line to an auxiliary config
                 extra["config4_powerlaw"] = {"error": str(e)[:200]}
-            cpu_gbps, cpu_dt, kind, sample, _ = cpu_reference_sampled(A, x, alg, 3, 1, budget_s=15.0)
+            cpu_gbps, cpu_dt, kind, sample, _ = cpu_reference_sampled(A, x, alg_step, 2, 1, calls_per_step=len(names),
+                                                                      budget_s=20.0)
             extra["cpu_baseline"] = {"value": round(cpu_gbps, 4), "unit": UNIT, "cores": 1, "kind": kind, "sample": sample}
         extra["variants"] = variants
-        cfg = workload_config("c2", HEADLINE, l2)
-        roof_alg, roof_us = alg, res["us_per_call"]
-        e2e_val = alg / e2e_s / 1e9
+        extra["step"] = names
+        cfg = workload_config("c2", "+".join(names), l2)
+        cfg["launch"] = ("CUDA graphs of %d steps replayed back to back" % min(GRAPH_STEPS, args.steps)) if GRAPH else "one stream launch per call"
+        roof_alg, roof_us, phys = algs[dominant], variants[dominant]["us_per_call"], physs[dominant]
+        roof_kernel = {"wsp": "wsp_ring_kernel<uint2>", "asp": "asp_kernel", "awsp": "panel_kernel<16,false,false,8>",
+                       "tcsr": "panel_kernel<16,true,false,8>"}[dominant]
+        e2e_val = alg_step / e2e_s / 1e9
         scaling = "weak"
-        traffic = ncu_traffic(f"c2/{HEADLINE}")
+        traffic = ncu_traffic(f"c2/{dominant}")
     else:
         # ---------------- multi GPU: config-5 slabs + all-gather ------------------------------
         res, plans, (dx, dy), x, (alg, phys) = slab_unit(torch, S, synth, rank, max(20, args.steps // 10), 5, stream)
@@ -409,6 +487,7 @@ def main():
         extra["variants"] = {HEADLINE + "_kernel_only_rank0": res}
         extra["allgather_bytes_per_step"] = world * C5_SLAB_N * 4
         roof_alg, roof_us = alg, res["us_per_call"]
+        roof_kernel = "panel_kernel<16,false,true,16>"
         scaling = "weak"
         traffic = ncu_traffic(f"c5/{HEADLINE}")
 
@@ -421,7 +500,7 @@ def main():
                 "us_per_call": round(ms / args.steps * 1e3, 3),
                 "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                              "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                             "kernel": "panel_kernel<8,false>" if world == 1 else "panel_kernel<16,false>",
+                             "kernel": roof_kernel,
                              "alg_bytes_per_launch": roof_alg,
                              "phys_bytes_per_launch": phys, "phys_frac": round(phys / (roof_us * 1e-6) / 1e9 / peak, 4)},
                 "e2e": {"value": round(e2e_val, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

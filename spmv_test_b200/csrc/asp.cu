@@ -128,8 +128,9 @@ int launch_asp(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st)
     return SPMV_OK;
 }
 
-// grid = (ceil(N/512), row splits): about three CTAs per SM (all resident at once: more splits
-// only add head/tail latency, measured), at least 64 rows per split.
+// grid = (ceil(N/512), row splits): a little over two CTAs per SM, all resident at once — every
+// CTA pays a fixed few microseconds (x compaction, first rows, split reduction), so more splits
+// are slower (measured: 8-12 splits 24.7 us, 16 splits 26.9 us on config 2) — at least 64 rows each.
 int configure_asp(spmv_plan *p, const spmv_options_t *o)
 {
     p->block = kAspThreads;
@@ -141,7 +142,7 @@ int configure_asp(spmv_plan *p, const spmv_options_t *o)
     const int64_t M = std::max<int64_t>(p->M, 1);
     int splits;
     if (o && o->row_splits > 0) splits = (int)std::min<int64_t>(o->row_splits, M);
-    else splits = std::max(1, (3 * p->sm_count + p->col_tiles / 2) / std::max(1, p->col_tiles));
+    else splits = std::max(1, (9 * p->sm_count / 4 + p->col_tiles / 2) / std::max(1, p->col_tiles));
     int rps = (int)((M + splits - 1) / splits);
     if (!(o && o->row_splits > 0)) rps = std::max(64, rps);
     rps = (rps + 31) / 32 * 32;

@@ -304,12 +304,11 @@ int choose_slab_cols(int64_t M, int64_t N, int64_t nnz)
     const double density = (double)nnz / ((double)M * (double)N);
     int w = kMinSlabCols;
     while (w < kMaxSlabCols && w * density < 300.0) w <<= 1;
-    // very sparse: segments stay short whatever the width and the kernel packs several rows per
-    // chunk anyway; 2048 columns keep the accumulator rows small enough for 8 warps and a
-    // 16-deep ring per SM
-    if (w == kMaxSlabCols && w * density < 80.0) w = 2048;
     const int64_t row_blocks = (M + kTileRows - 1) / kTileRows;
     while (w > kMinSlabCols && ((N + w - 1) / w) * row_blocks < 1024) w >>= 1;
+    // and at least ~10 slabs: the kernel's CTAs are spread over the slabs, and the last CTA of
+    // a slab adds all of that slab's partial rows, so few wide slabs mean a long serial tail
+    while (w > kMinSlabCols && N / w < 10) w >>= 1;
     return w;
 }
 

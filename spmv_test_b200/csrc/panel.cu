@@ -31,8 +31,8 @@ namespace {
 
 constexpr int kPanelMaxWarps = 8;
 constexpr int kPanelThreads = kPanelMaxWarps * 32;   // launch bound; the CTA size is a plan parameter
-// chunks in flight per warp (cp.async groups): 8 in single-row mode, 16 in multi-row mode,
-// where accumulator rows leave room for fewer warps and the ring has to carry the latency
+// chunks in flight per warp (cp.async groups)
+constexpr int kRingStages = 8;
 
 template <int IDXB> struct ColIdx;
 template <> struct ColIdx<8> {
@@ -63,8 +63,7 @@ template <> struct ColIdx<16> {
 // per-warp shared memory: [acc: W floats][vals ring: kStages x 32 float4][idx ring][list: 128 x uint4]
 //                         [slot info][multi-row mode: per-lane (x, row slot) ring]
 constexpr int kListCap = 128;              // rows a warp can take from one metadata batch
-constexpr int kStreamMinActive = 11;       // active rows (of 32) from which a block is streamed whole
-constexpr int kMetaBatch = 4;              // 32-row blocks of metadata fetched together
+constexpr int kMetaBatch = 8;              // 32-row blocks of metadata fetched together
 template <int IDXB, int kStages> __host__ __device__ constexpr int warp_smem_bytes(int W)
 {
     return W * 4 + kStages * 32 * 16 + kStages * 32 * (IDXB == 8 ? 4 : 8) + kListCap * 16 + kStages * 8 + kStages * 32 * 8;
@@ -252,42 +251,36 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         const int bstep = by_block ? n_warps : 1;
         const int bfirst = blk_a + (by_block ? warp : 0);
         int rank_base = 0;
-        Meta nxt[kMetaBatch];
-#pragma unroll
-        for (int j = 0; j < kMetaBatch; j++)
-            if (bfirst + j * bstep < blk_b) nxt[j] = load_meta(slab, bfirst + j * bstep);
         for (int blk0 = bfirst; blk0 < blk_b; blk0 += kMetaBatch * bstep) {
+            // metadata of kMetaBatch blocks at once (one latency per 256 rows; a short piece
+            // is covered by a single batch), consumed as two lists of four blocks
             Meta cur[kMetaBatch];
 #pragma unroll
-            for (int j = 0; j < kMetaBatch; j++) cur[j] = nxt[j];
-#pragma unroll
             for (int j = 0; j < kMetaBatch; j++)
-                if (blk0 + (kMetaBatch + j) * bstep < blk_b) nxt[j] = load_meta(slab, blk0 + (kMetaBatch + j) * bstep);
-            int cnt = 0;
+                if (blk0 + j * bstep < blk_b) cur[j] = load_meta(slab, blk0 + j * bstep);
 #pragma unroll
-            for (int j = 0; j < kMetaBatch; j++) {
-                const int blk = blk0 + j * bstep;
-                const int row = blk * 32 + lane;
-                const bool nonempty = blk < blk_b && row >= row_a && row < row_b && cur[j].g1 > cur[j].g0;
-                const bool active = nonempty && cur[j].xv != 0.0f;
-                // Short segments with many active rows (multi-row mode, block owned outright):
-                // fetching only the active rows would read scattered ~100-byte pieces, which
-                // DRAM serves at a fraction of its bandwidth (measured), so the whole block is
-                // streamed contiguously and the inactive rows are skipped in the arithmetic only.
-                const bool stream = MR && by_block && __popc(__ballot_sync(kFull, active)) >= kStreamMinActive;
-                const bool valid = stream ? nonempty : active;
-                const unsigned mask = __ballot_sync(kFull, valid);
-                const int rank = rank_base + __popc(mask & lt);
-                const bool mine = valid && (by_block || (rank & (n_warps - 1)) == warp);   // n_warps is a power of two
-                const unsigned mm = __ballot_sync(kFull, mine);
-                if (mine) list[cnt + __popc(mm & lt)] = make_uint4(cur[j].g0, cur[j].g1, __float_as_uint(cur[j].xv), 0u);
-                cnt += __popc(mm);
-                rank_base += __popc(mask);
+            for (int half = 0; half < 2; half++) {
+                if (blk0 + half * (kMetaBatch / 2) * bstep >= blk_b) break;
+                int cnt = 0;
+#pragma unroll
+                for (int jj = 0; jj < kMetaBatch / 2; jj++) {
+                    const int j = half * (kMetaBatch / 2) + jj;
+                    const int blk = blk0 + j * bstep;
+                    const int row = blk * 32 + lane;
+                    const bool valid = blk < blk_b && row >= row_a && row < row_b && cur[j].xv != 0.0f && cur[j].g1 > cur[j].g0;
+                    const unsigned mask = __ballot_sync(kFull, valid);
+                    const int rank = rank_base + __popc(mask & lt);
+                    const bool mine = valid && (by_block || (rank & (n_warps - 1)) == warp);   // n_warps is a power of two
+                    const unsigned mm = __ballot_sync(kFull, mine);
+                    if (mine) list[cnt + __popc(mm & lt)] = make_uint4(cur[j].g0, cur[j].g1, __float_as_uint(cur[j].xv), 0u);
+                    cnt += __popc(mm);
+                    rank_base += __popc(mask);
+                }
+                __syncwarp();
+                if (piece == 0 && blk0 == bfirst && half == 0) SPMV_STAMP(wg, 1);
+                if (MR) run_list_mr(cnt); else run_list(cnt);
+                __syncwarp();                             // the list is rewritten next
             }
-            __syncwarp();
-            if (piece == 0 && blk0 == bfirst) SPMV_STAMP(wg, 1);
-            if (MR) run_list_mr(cnt); else run_list(cnt);
-            __syncwarp();                                 // the list is rewritten next
         }
         SPMV_STAMP(wg, 2);
         cp_async_wait<0>();
@@ -337,9 +330,12 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
 template <int IDXB, bool TILED, bool MR>
 int launch_variant(spmv_plan *p, const float *x, float *y, cudaStream_t st)
 {
-    auto k = panel_kernel<IDXB, TILED, MR, MR ? 16 : 8>;
-    if (p->smem > 48 * 1024)
+    auto k = panel_kernel<IDXB, TILED, MR, kRingStages>;
+    static int smem_set[16] = {0};                        // per device: largest dynamic smem opted in so far
+    if (p->smem > 48 * 1024 && p->device >= 0 && p->device < 16 && smem_set[p->device] < p->smem) {
         SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem));
+        smem_set[p->device] = p->smem;
+    }
     const DevPanel &d = p->panel;
     k<<<p->grid, p->block, p->smem, st>>>(reinterpret_cast<const float4 *>(d.vals), d.idx, d.off, d.rel, x, y,
                                          p->partial, p->tickets, (int)p->M, (int)p->N, d.slab_cols,
@@ -381,8 +377,7 @@ int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o)
     if (o && o->chunk_mode == 1) d.multirow = false;
     if (o && o->chunk_mode == 2) d.multirow = true;
     const int smem_cap = p->max_smem_optin > 0 ? p->max_smem_optin : 227 * 1024;
-    const int per_warp = d.multirow ? (h.index_bits == 8 ? warp_smem_bytes<8, 16>(h.slab_cols) : warp_smem_bytes<16, 16>(h.slab_cols))
-                                    : (h.index_bits == 8 ? warp_smem_bytes<8, 8>(h.slab_cols) : warp_smem_bytes<16, 8>(h.slab_cols));
+    const int per_warp = h.index_bits == 8 ? warp_smem_bytes<8, kRingStages>(h.slab_cols) : warp_smem_bytes<16, kRingStages>(h.slab_cols);
     int warps = 8;
     if (o && o->warps_per_col > 0) {
         warps = 1;

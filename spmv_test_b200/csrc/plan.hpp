@@ -101,6 +101,10 @@ struct spmv_plan {
     float *d_x = nullptr, *d_y = nullptr;
     cudaStream_t stream = nullptr;  // owned, used by spmv_run_host
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // spmv_run_host with the same pinned (x, y) pair again: H2D + kernels + D2H replayed as one graph
+    const float *graph_x = nullptr;
+    float *graph_y = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
 };
 
 namespace spmv {

@@ -273,7 +273,11 @@ static int launch_one(const spmv_plan *p, const WspBinDev &b, const float *x, fl
                       size_t smem, int x_bulk_ok)
 {
     auto k = wsp_kernel<IdxVec, T, XS>;
-    if (smem > 48 * 1024) SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int smem_set[16] = {0};
+    if (smem > 48 * 1024 && p->device >= 0 && p->device < 16 && smem_set[p->device] < (int)smem) {
+        SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[p->device] = (int)smem;
+    }
     k<<<b.grid, kWspBlock, smem, st>>>(reinterpret_cast<const float4 *>(p->wsp.vals),
                                        reinterpret_cast<const IdxVec *>(p->wsp.idx), p->wsp.colptr, b.cols,
                                        b.ncols, x, y, (uint32_t)p->M, x_bulk_ok);
@@ -301,7 +305,11 @@ template <typename IdxVec>
 static int launch_ring(const spmv_plan *p, const WspBinDev &b, const float *x, float *y, cudaStream_t st, int ok)
 {
     auto k = wsp_ring_kernel<IdxVec>;
-    if (b.smem > 48 * 1024) SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, b.smem));
+    static int smem_set[16] = {0};
+    if (b.smem > 48 * 1024 && p->device >= 0 && p->device < 16 && smem_set[p->device] < b.smem) {
+        SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, b.smem));
+        smem_set[p->device] = b.smem;
+    }
     k<<<b.grid, kRingWarps * 32, b.smem, st>>>(reinterpret_cast<const float4 *>(p->wsp.vals),
                                               reinterpret_cast<const IdxVec *>(p->wsp.idx), p->wsp.colptr, b.cols,
                                               b.ncols, x, y, (uint32_t)p->M, ok, p->smem);

@@ -92,11 +92,11 @@ def test_panel_slab_widths(slab):
 def test_panel_slab_auto_from_density():
     import spmv_test_b200 as S
     assert S.pack_dump("awsp", ob.gen_matrix(2048, 2048, 0.7, 1)).slab_cols == 256
-    wide = S.pack_dump("awsp", ob.gen_matrix(4096, 8192, 0.99, 2))      # few work units: narrowed to 1024
-    assert wide.slab_cols == 1024 and wide.index_bits == 16
+    wide = S.pack_dump("awsp", ob.gen_matrix(4096, 8192, 0.99, 2))      # few slabs / work units: narrowed
+    assert wide.slab_cols == 512 and wide.index_bits == 16
     from spmv_test_b200 import synth
-    cp, ri, va = synth.bernoulli_csc(32768, 65536, 0.01, 9)               # config-5 family: 2048 (multi-row chunks)
-    assert S.pack_dump("awsp", csc=(cp, ri, va), shape=(32768, 65536)).slab_cols == 2048
+    cp, ri, va = synth.bernoulli_csc(32768, 65536, 0.01, 9)               # config-5 family: widest slabs
+    assert S.pack_dump("awsp", csc=(cp, ri, va), shape=(32768, 65536)).slab_cols == 4096
 
 
 @pytest.mark.parametrize("M,N,sa", CASES)
