@@ -153,6 +153,20 @@ SPMV_API int spmv_plan_traffic(const spmv_plan_t *plan, const float *x, double *
 SPMV_API int spmv_run(spmv_plan_t *plan, const float *d_x, float *d_y, void *stream);
 
 /*
+ * Column-sharded multi-GPU execution with the all-gather fused into the kernel epilogue
+ * (the reference is single-GPU).  This rank's plan covers the output columns
+ * [offset, offset + N) of the full y; its final stores go to that slice of EVERY rank's copy of
+ * y: d_y_dst[k] (k < n_dst <= 8) are the base pointers of the ranks' full-y buffers as mapped
+ * into this process (peer-accessible / symmetric memory, e.g. torch symmetric memory
+ * buffer_ptrs); if d_y_multicast is non-NULL it is the NVSwitch multicast alias of those buffers
+ * and one multimem.st per element replaces the n_dst peer stores.  The caller separates
+ * consecutive calls with a cross-rank barrier (and alternates two y buffers), exactly as it
+ * would around an all-gather.  With n_dst = 1 and offset = 0 this is spmv_run.
+ */
+SPMV_API int spmv_run_scatter(spmv_plan_t *plan, const float *d_x, int n_dst, float *const *d_y_dst,
+                              float *d_y_multicast, int64_t offset, void *stream);
+
+/*
  * Host-buffer convenience: H2D x, run, D2H y, synchronise — the per-call part of a
  * reference launcher once the matrix is resident (awsp.cu:342-381).  If timing_ms is
  * non-NULL it receives the device time of the kernel(s) alone (the region the

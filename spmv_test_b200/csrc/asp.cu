@@ -28,7 +28,7 @@ constexpr int kAspChunk = 1024;               // rows compacted per pass
 constexpr int kAspStages = 16;             // rows in flight per warp
 
 __global__ void __launch_bounds__(kAspThreads)
-asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ x, float *__restrict__ y,
+asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ x, const YDst yd,
            float *__restrict__ partial, unsigned *__restrict__ tickets, int M, int N, int rows_per_split,
            int splits)
 {
@@ -106,23 +106,23 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
     }
 
     if (splits == 1) {
-        if (col_ok) *reinterpret_cast<float4 *>(y + c0) = acc;
+        if (col_ok) y_store4(yd, (size_t)c0 >> 2, acc);
         return;
     }
     const size_t npad = (size_t)gridDim.x * kAspTile;
     *reinterpret_cast<float4 *>(partial + (size_t)split * npad + (size_t)tile * kAspTile + tid * 4) = acc;
     const int n_valid = min(kAspTile, N - tile * kAspTile);
     __syncthreads();                                      // the row list is dead: reuse it as scratch
-    split_reduce_finish(y, partial, tickets, tile, splits, kAspTile, n_valid, npad, &last_flag,
+    split_reduce_finish(yd, partial, tickets, tile, splits, kAspTile, n_valid, npad, &last_flag,
                         reinterpret_cast<float4 *>(rows_s));
 }
 
 } // namespace
 
-int launch_asp(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st)
+int launch_asp(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st)
 {
     if (p->N == 0) return SPMV_OK;
-    asp_kernel<<<p->grid, kAspThreads, 0, st>>>(p->asp.A, (long long)p->asp.ld, d_x, d_y, p->partial, p->tickets,
+    asp_kernel<<<p->grid, kAspThreads, 0, st>>>(p->asp.A, (long long)p->asp.ld, d_x, yd, p->partial, p->tickets,
                                                (int)p->M, (int)p->N, p->asp.rows_per_split, p->row_splits);
     SPMV_CUDA(cudaGetLastError());
     return SPMV_OK;

@@ -366,19 +366,44 @@ int spmv_plan_traffic(const spmv_plan_t *p, const float *x, double *alg_bytes, d
     return SPMV_OK;
 }
 
+static int run_to(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st)
+{
+    switch (p->variant) {
+    case SPMV_WSP: return launch_wsp(p, d_x, yd, st);
+    case SPMV_ASP: return launch_asp(p, d_x, yd, st);
+    case SPMV_AWSP:
+    case SPMV_TCSR: return launch_panel(p, d_x, yd, st);
+    }
+    return set_error(SPMV_ERR_ARG, "corrupt plan");
+}
+
 int spmv_run(spmv_plan_t *p, const float *d_x, float *d_y, void *stream)
 {
     if (!p) return set_error(SPMV_ERR_ARG, "null plan");
     if ((!d_x && p->M > 0) || (!d_y && p->N > 0)) return set_error(SPMV_ERR_ARG, "null device vector");
     if ((reinterpret_cast<uintptr_t>(d_y) & 15) != 0) return set_error(SPMV_ERR_ARG, "d_y must be 16-byte aligned");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    switch (p->variant) {
-    case SPMV_WSP: return launch_wsp(p, d_x, d_y, st);
-    case SPMV_ASP: return launch_asp(p, d_x, d_y, st);
-    case SPMV_AWSP:
-    case SPMV_TCSR: return launch_panel(p, d_x, d_y, st);
+    YDst yd{};
+    yd.p[0] = d_y; yd.n = 1; yd.mc = nullptr;
+    return run_to(p, d_x, yd, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int spmv_run_scatter(spmv_plan_t *p, const float *d_x, int n_dst, float *const *d_y_dst, float *d_y_multicast,
+                     int64_t offset, void *stream)
+{
+    if (!p) return set_error(SPMV_ERR_ARG, "null plan");
+    if (!d_x && p->M > 0) return set_error(SPMV_ERR_ARG, "null device vector");
+    if (n_dst < 1 || n_dst > kMaxYDst || !d_y_dst) return set_error(SPMV_ERR_ARG, "1..%d destinations required", kMaxYDst);
+    if (offset < 0 || offset % 4) return set_error(SPMV_ERR_ARG, "offset must be a non-negative multiple of 4 floats");
+    YDst yd{};
+    yd.n = n_dst;
+    for (int k = 0; k < n_dst; k++) {
+        if (!d_y_dst[k] || (reinterpret_cast<uintptr_t>(d_y_dst[k]) & 15) != 0)
+            return set_error(SPMV_ERR_ARG, "destination %d is null or not 16-byte aligned", k);
+        yd.p[k] = d_y_dst[k] + offset;
     }
-    return set_error(SPMV_ERR_ARG, "corrupt plan");
+    yd.mc = d_y_multicast ? d_y_multicast + offset : nullptr;
+    if (yd.mc && (reinterpret_cast<uintptr_t>(yd.mc) & 15) != 0) return set_error(SPMV_ERR_ARG, "multicast pointer not 16-byte aligned");
+    return run_to(p, d_x, yd, reinterpret_cast<cudaStream_t>(stream));
 }
 
 static bool is_pinned_host(const void *ptr)

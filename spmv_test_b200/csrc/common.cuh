@@ -7,7 +7,7 @@ namespace spmv {
 
 // ---- development-only timeline (tools/trace_build.sh builds a -DSPMV_TRACE library) -------
 #ifdef SPMV_TRACE
-constexpr int kTraceSlots = 8;
+constexpr int kTraceSlots = 10;
 constexpr int kTraceWarps = 1 << 16;
 extern __device__ unsigned long long g_trace[kTraceWarps * kTraceSlots];
 __device__ __forceinline__ void trace_stamp(int warp_global, int slot)
@@ -18,10 +18,54 @@ __device__ __forceinline__ void trace_stamp(int warp_global, int slot)
         g_trace[(size_t)warp_global * kTraceSlots + slot] = t;
     }
 }
+__device__ __forceinline__ void trace_smid(int warp_global, int slot)
+{
+    if ((threadIdx.x & 31) == 0 && warp_global < kTraceWarps) {
+        unsigned id;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(id));
+        g_trace[(size_t)warp_global * kTraceSlots + slot] = id;
+    }
+}
 #define SPMV_STAMP(w, s) ::spmv::trace_stamp((w), (s))
+#define SPMV_STAMP_SMID(w, s) ::spmv::trace_smid((w), (s))
 #else
 #define SPMV_STAMP(w, s) ((void)0)
+#define SPMV_STAMP_SMID(w, s) ((void)0)
 #endif
+
+// ---- destinations of y ------------------------------------------------------------------------
+// Single GPU: one pointer.  Column-sharded multi-GPU: the kernel's final
+// stores go straight into every rank's copy of the full y — one multimem.st through the NVSwitch
+// multicast address when there is one (NVLS), else one peer store per rank over NVLink — so the
+// all-gather is fused into the epilogue and no separate collective kernel runs.
+constexpr int kMaxYDst = 8;
+struct YDst {
+    float *p[kMaxYDst];      // base pointers, already offset to this rank's slice
+    float *mc;               // multicast alias of the same slice (or null)
+    int n;
+};
+__device__ __forceinline__ void y_store(const YDst &d, size_t i, float v)
+{
+    if (d.mc) {
+        asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(d.mc + i), "r"(__float_as_uint(v)) : "memory");
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < d.n; k++) d.p[k][i] = v;
+    }
+}
+__device__ __forceinline__ void y_store4(const YDst &d, size_t i4, float4 v)   // i4: index in float4 units
+{
+    if (d.mc) {
+        unsigned long long lo, hi;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(lo) : "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(hi) : "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)));
+        asm volatile("multimem.st.weak.global.b64 [%0], %1;" ::"l"(d.mc + i4 * 4), "l"(lo) : "memory");
+        asm volatile("multimem.st.weak.global.b64 [%0], %1;" ::"l"(d.mc + i4 * 4 + 2), "l"(hi) : "memory");
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < d.n; k++) reinterpret_cast<float4 *>(d.p[k])[i4] = v;
+    }
+}
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
@@ -178,7 +222,7 @@ __device__ __forceinline__ float4 f4_add(float4 a, float4 b)
 }
 
 template <class RowFn>
-__device__ __forceinline__ bool split_reduce_rows(float *__restrict__ y_tile, RowFn row, unsigned *__restrict__ ticket,
+__device__ __forceinline__ bool split_reduce_rows(const YDst &yd, size_t tile_off, RowFn row, unsigned *__restrict__ ticket,
                                                   int rows, int width, int n_valid, int *smem_flag, float4 *scratch)
 {
     __threadfence();      // publish this CTA's partial row
@@ -208,7 +252,7 @@ __device__ __forceinline__ bool split_reduce_rows(float *__restrict__ y_tile, Ro
         }
         return acc;
     };
-    float4 *out = reinterpret_cast<float4 *>(y_tile);
+    const size_t out4 = tile_off >> 2;                    // tile offsets are multiples of 4 floats
     if (T >= 2 * V) {
         const int K = T / V, k = threadIdx.x / V, v = threadIdx.x - k * V;
         if (k < K) scratch[threadIdx.x] = sum_rows(v, k, K);
@@ -216,22 +260,22 @@ __device__ __forceinline__ bool split_reduce_rows(float *__restrict__ y_tile, Ro
         if (k == 0 && v * 4 < n_valid) {
             float4 acc = scratch[v];
             for (int j = 1; j < K; j++) acc = f4_add(acc, scratch[j * V + v]);
-            out[v] = acc;
+            y_store4(yd, out4 + v, acc);
         }
     } else {
-        for (int v = threadIdx.x; v * 4 < n_valid; v += T) out[v] = sum_rows(v, 0, 1);
+        for (int v = threadIdx.x; v * 4 < n_valid; v += T) y_store4(yd, out4 + v, sum_rows(v, 0, 1));
     }
     return true;
 }
 
 // regular layout: partial[split][tile*width ..], split stride `split_stride` floats
-__device__ __forceinline__ bool split_reduce_finish(float *__restrict__ y, const float *__restrict__ partial,
+__device__ __forceinline__ bool split_reduce_finish(const YDst &yd, const float *__restrict__ partial,
                                                      unsigned *__restrict__ tickets, int tile, int splits,
                                                      int width, int n_valid, size_t split_stride,
                                                      int *smem_flag, float4 *scratch)
 {
     const float *base = partial + (size_t)tile * width;
-    return split_reduce_rows(y + (size_t)tile * width, [&](int j) { return base + (size_t)j * split_stride; },
+    return split_reduce_rows(yd, (size_t)tile * width, [&](int j) { return base + (size_t)j * split_stride; },
                              &tickets[tile], splits, width, n_valid, smem_flag, scratch);
 }
 

@@ -83,7 +83,7 @@ template <int IDXB, bool TILED, bool MR, int kStages>
 __global__ void __launch_bounds__(kPanelThreads)
 panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
              const uint32_t *__restrict__ off, const uint16_t *__restrict__ rel,
-             const float *__restrict__ x, float *__restrict__ y, float *__restrict__ partial,
+             const float *__restrict__ x, const YDst yd, float *__restrict__ partial,
              unsigned *__restrict__ tickets, int M, int N, int W, int row_blocks, int slabs, int kmax)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -104,6 +104,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     const int wg = blockIdx.x * n_warps + warp;           // trace id
     (void)wg;
     SPMV_STAMP(wg, 0);
+    SPMV_STAMP_SMID(wg, 8);
 
     const long long T = (long long)slabs * M, G = gridDim.x;
     const long long u_begin = range_begin(blockIdx.x, T, G), u_end = range_begin(blockIdx.x + 1, T, G);
@@ -301,11 +302,11 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         const int n_valid = min(W, N - col0);
         const int wstride = warp_smem_bytes<IDXB, kStages>(W) / 4;
         const float *acc0 = reinterpret_cast<const float *>(smem_raw);
-        float *dst = n_pieces == 1 ? y + col0 : partial + ((size_t)blockIdx.x * kmax + piece) * W;
+        float *dst = partial + ((size_t)blockIdx.x * kmax + piece) * W;
         for (int c = tid; c < n_valid; c += blockDim.x) {
             float s = acc0[c];
             for (int w = 1; w < n_warps; w++) s += acc0[(size_t)w * wstride + c];
-            dst[c] = s;
+            if (n_pieces == 1) y_store(yd, (size_t)col0 + c, s); else dst[c] = s;
         }
         SPMV_STAMP(wg, 6);
         if (n_pieces > 1) {
@@ -319,7 +320,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
                 row_of[j] = (uint32_t)(c * kmax + (slab - (int)(range_begin(c, T, G) / M)));
             }
             // (split_reduce_rows starts with a barrier, which also publishes row_of)
-            split_reduce_rows(y + col0, [&](int j) { return partial + (size_t)row_of[j] * W; }, &tickets[slab],
+            split_reduce_rows(yd, (size_t)col0, [&](int j) { return partial + (size_t)row_of[j] * W; }, &tickets[slab],
                               n_pieces, W, n_valid, &last_flag, scratch);
         }
         __syncthreads();                                  // shared memory is reused by the next piece
@@ -328,7 +329,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
 }
 
 template <int IDXB, bool TILED, bool MR>
-int launch_variant(spmv_plan *p, const float *x, float *y, cudaStream_t st)
+int launch_variant(spmv_plan *p, const float *x, const YDst &y, cudaStream_t st)
 {
     auto k = panel_kernel<IDXB, TILED, MR, kRingStages>;
     static int smem_set[16] = {0};                        // per device: largest dynamic smem opted in so far
@@ -346,11 +347,11 @@ int launch_variant(spmv_plan *p, const float *x, float *y, cudaStream_t st)
 
 } // namespace
 
-int launch_panel(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st)
+int launch_panel(spmv_plan *p, const float *d_x, const YDst &d_y, cudaStream_t st)
 {
     if (p->N == 0) return SPMV_OK;
-    if (p->M == 0) {                                      // no rows: y = 0
-        SPMV_CUDA(cudaMemsetAsync(d_y, 0, (size_t)p->N * sizeof(float), st));
+    if (p->M == 0) {                                      // no rows: y = 0 (plain stores; the caller joins)
+        for (int k = 0; k < d_y.n; k++) SPMV_CUDA(cudaMemsetAsync(d_y.p[k], 0, (size_t)p->N * sizeof(float), st));
         return SPMV_OK;
     }
     const DevPanel &d = p->panel;

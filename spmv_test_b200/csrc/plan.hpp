@@ -109,9 +109,10 @@ struct spmv_plan {
 
 namespace spmv {
 // kernel launchers (one per .cu); all are asynchronous on `st`
-int launch_wsp(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st);
-int launch_asp(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st);
-int launch_panel(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st);
+struct YDst;   // common.cuh: where y goes (one pointer, or every rank's copy in the sharded case)
+int launch_wsp(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
+int launch_asp(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
+int launch_panel(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
 int launch_compact(const float *d_x, int64_t M, int32_t *d_idx, float *d_val, int32_t *d_count,
                    void *d_scratch, size_t scratch_bytes, cudaStream_t st);
 size_t compact_scratch_bytes(int64_t M);

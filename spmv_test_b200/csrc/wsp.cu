@@ -49,7 +49,7 @@ template <typename IdxVec, int T, bool XS>
 __global__ void __launch_bounds__(kWspBlock)
 wsp_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
            const uint32_t *__restrict__ colptr, const int32_t *__restrict__ cols, int ncols,
-           const float *__restrict__ x, float *__restrict__ y, uint32_t M, int x_bulk_ok)
+           const float *__restrict__ x, const YDst yd, uint32_t M, int x_bulk_ok)
 {
     extern __shared__ __align__(16) float xs[];          // M + 1 (+pad) floats when XS
     __shared__ __align__(8) uint64_t bar;
@@ -121,7 +121,7 @@ wsp_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
         if (T >= 32) {
             acc = warp_sum(acc);
             if (T == 32) {
-                if (lane == 0) y[c] = acc;
+                if (lane == 0) y_store(yd, c, acc);
             } else {
                 constexpr int W = T / 32;                 // warps per team
                 const int wt = (tid / 32) % (W > 0 ? W : 1);
@@ -131,14 +131,14 @@ wsp_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
                 if (wt == 0 && lane == 0) {
                     float s = 0.f;
                     for (int w = 0; w < W; w++) s += red[team_local * W + w];
-                    y[c] = s;
+                    y_store(yd, c, s);
                 }
                 asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(T) : "memory");
             }
         } else {
 #pragma unroll
             for (int s = T / 2; s >= 1; s >>= 1) acc += __shfl_xor_sync(kFull, acc, s);
-            if (tl == 0) y[c] = acc;
+            if (tl == 0) y_store(yd, c, acc);
         }
     }
 }
@@ -164,7 +164,7 @@ template <typename IdxVec>
 __global__ void __launch_bounds__(kRingWarps * 32)
 wsp_ring_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
                 const uint32_t *__restrict__ colptr, const int32_t *__restrict__ cols, int ncols,
-                const float *__restrict__ x, float *__restrict__ y, uint32_t M, int x_bulk_ok, int xs_bytes)
+                const float *__restrict__ x, const YDst yd, uint32_t M, int x_bulk_ok, int xs_bytes)
 {
     extern __shared__ __align__(16) unsigned char wsm[];
     __shared__ __align__(8) uint64_t bar;
@@ -245,7 +245,7 @@ wsp_ring_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
                 a2 = fmaf(v.z, xs[i[2]], a2); a3 = fmaf(v.w, xs[i[3]], a3);
                 if (fin[s] >= 0) {
                     const float t = warp_sum((a0 + a1) + (a2 + a3));
-                    if (lane == 0) y[fin[s]] = t;
+                    if (lane == 0) y_store(yd, fin[s], t);
                     a0 = a1 = a2 = a3 = 0.f;
                 }
             }
@@ -269,7 +269,7 @@ struct WspState {            // hangs off the plan through plan->wsp_state
 };
 
 template <typename IdxVec, int T, bool XS>
-static int launch_one(const spmv_plan *p, const WspBinDev &b, const float *x, float *y, cudaStream_t st,
+static int launch_one(const spmv_plan *p, const WspBinDev &b, const float *x, const YDst &y, cudaStream_t st,
                       size_t smem, int x_bulk_ok)
 {
     auto k = wsp_kernel<IdxVec, T, XS>;
@@ -286,7 +286,7 @@ static int launch_one(const spmv_plan *p, const WspBinDev &b, const float *x, fl
 }
 
 template <typename IdxVec, bool XS>
-static int launch_T(const spmv_plan *p, const WspBinDev &b, const float *x, float *y, cudaStream_t st,
+static int launch_T(const spmv_plan *p, const WspBinDev &b, const float *x, const YDst &y, cudaStream_t st,
                     size_t smem, int ok)
 {
     switch (b.T) {
@@ -302,7 +302,7 @@ static int launch_T(const spmv_plan *p, const WspBinDev &b, const float *x, floa
 }
 
 template <typename IdxVec>
-static int launch_ring(const spmv_plan *p, const WspBinDev &b, const float *x, float *y, cudaStream_t st, int ok)
+static int launch_ring(const spmv_plan *p, const WspBinDev &b, const float *x, const YDst &y, cudaStream_t st, int ok)
 {
     auto k = wsp_ring_kernel<IdxVec>;
     static int smem_set[16] = {0};
@@ -317,7 +317,7 @@ static int launch_ring(const spmv_plan *p, const WspBinDev &b, const float *x, f
     return SPMV_OK;
 }
 
-int launch_wsp(spmv_plan *p, const float *d_x, float *d_y, cudaStream_t st)
+int launch_wsp(spmv_plan *p, const float *d_x, const YDst &d_y, cudaStream_t st)
 {
     if (p->N == 0) return SPMV_OK;
     const WspState *s = reinterpret_cast<const WspState *>(p->wsp_state);

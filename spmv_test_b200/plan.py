@@ -113,6 +113,18 @@ class Plan:
             stream = torch.cuda.current_stream().cuda_stream
         check(lib().spmv_run(self._h, C.c_void_p(px), C.c_void_p(py), C.c_void_p(stream)))
 
+    def run_scatter(self, d_x, dst_ptrs, offset, multicast_ptr=0, stream=None):
+        """y slice of this rank -> [offset, offset+N) of every buffer in dst_ptrs (device pointers
+        of all ranks' full-y buffers), or through the multicast alias when given: the all-gather
+        fused into the kernel epilogue."""
+        px = d_x if isinstance(d_x, int) else d_x.data_ptr()
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        arr = (C.c_void_p * len(dst_ptrs))(*[int(q) for q in dst_ptrs])
+        check(lib().spmv_run_scatter(self._h, C.c_void_p(px), len(dst_ptrs), arr, C.c_void_p(int(multicast_ptr) or None),
+                                     int(offset), C.c_void_p(stream)))
+
     def run_host(self, x, y=None, timing=False):
         """Host-buffer call (H2D x, kernels, D2H y, synchronise) — the per-call part of a
         reference launcher.  Returns y (and the kernels' device milliseconds if timing)."""

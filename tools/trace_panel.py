@@ -35,11 +35,13 @@ nw = info["grid_x"] * info["grid_y"] * 8
 for i in range(9):
     plans[i % 4].run(dx, dy, st.cuda_stream)
 st.synchronize()
-buf = np.zeros(nw * 8, np.uint64)
+buf = np.zeros(nw * 10, np.uint64)
 L = S.lib()
 L.spmv_trace_read.argtypes = [C.c_void_p, C.c_int64]
 assert L.spmv_trace_read(C.c_void_p(buf.ctypes.data), buf.size) == 0
-t = buf.reshape(nw, 8).astype(np.int64)
+raw = buf.reshape(nw, 10).astype(np.int64)
+smid = raw[:, 8]
+t = raw[:, :8]
 t0 = t[:, 0].min()
 t = (t - t0) / 1e3
 names = ["start", "meta", "issued", "first", "streamed", "cta_bar", "partial", "end"]
@@ -49,3 +51,13 @@ for k, n in enumerate(names):
 d = np.diff(t, axis=1)
 print("phase medians (us):", {names[k + 1]: round(float(np.median(d[:, k])), 2) for k in range(7)})
 print("phase p90 (us):    ", {names[k + 1]: round(float(np.percentile(d[:, k], 90)), 2) for k in range(7)})
+
+# stragglers: the warps that finish streaming last
+order = np.argsort(-t[:, 4])[:12]
+for w in order:
+    print(f"warp {w:5d} cta {w // 8:4d} sm {smid[w]:3d}  " + " ".join(f"{names[k]}={t[w, k]:.1f}" for k in range(8)))
+per_sm = {}
+for w in range(nw):
+    per_sm.setdefault(int(smid[w]), []).append(t[w, 4])
+ends = sorted((max(v), k, len(v)) for k, v in per_sm.items())
+print("SMs by last 'streamed':", [(k, n, round(e, 1)) for e, k, n in ends[-8:]], " fastest:", [(k, n, round(e, 1)) for e, k, n in ends[:4]])
