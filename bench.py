@@ -437,22 +437,44 @@ def main():
         def local_run(d_x, d_y):
             plans[state["i"] % n].run(d_x, d_y, torch.cuda.current_stream().cuda_stream)
             state["i"] += 1
-        sh = S.ShardedSgemv(bounds, rank, world, plan=plans[0], local_run=local_run)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            for _ in range(args.warmup):
-                y_full = sh.run(dx)
-            stream.synchronize()
-            dist.barrier()
-            torch.cuda.synchronize()
-            e0.record(stream)
-            for _ in range(args.steps):
-                y_full = sh.run(dx)
-            e1.record(stream)
-            stream.synchronize()
-            torch.cuda.synchronize()
-            dist.barrier()
-        t = torch.tensor([e0.elapsed_time(e1), alg, phys], dtype=torch.float64, device="cuda")
+        class _Rot:                                       # the sharded runner sees a rotating plan
+            def run(self, d_x, d_y, stream=None):
+                local_run(d_x, d_y)
+
+            def run_scatter(self, d_x, ptrs, offset, mc=0, stream=None):
+                plans[state["i"] % n].run_scatter(d_x, ptrs, offset, mc, torch.cuda.current_stream().cuda_stream)
+                state["i"] += 1
+        rot = _Rot()
+
+        def timed_join(join):
+            sh = S.ShardedSgemv(bounds, rank, world, plan=rot, join=join)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                for _ in range(args.warmup):
+                    y_full = sh.run(dx)
+                stream.synchronize()
+                dist.barrier()
+                torch.cuda.synchronize()
+                e0.record(stream)
+                for _ in range(args.steps):
+                    y_full = sh.run(dx)
+                e1.record(stream)
+                stream.synchronize()
+                torch.cuda.synchronize()
+                dist.barrier()
+            return sh, y_full, e0.elapsed_time(e1)
+
+        sh_nccl, y_nccl, ms_nccl = timed_join("nccl")
+        try:
+            sh, y_full, ms_fused = timed_join("fused")
+            assert torch.equal(y_full, y_nccl), "fused epilogue and NCCL all-gather disagree"
+            join_used = "fused epilogue (%s stores into symmetric memory + barrier)" % ("multicast" if sh.multicast else "peer")
+        except Exception as e:                            # no symmetric memory on this box: NCCL join
+            sh, y_full, ms_fused = sh_nccl, y_nccl, None
+            join_used = "nccl all_gather (fused epilogue unavailable: %s)" % str(e)[:120]
+        ms_join = ms_fused if ms_fused is not None else ms_nccl
+        e_ms = torch.tensor([ms_join], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms_join, alg, phys], dtype=torch.float64, device="cuda")
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -486,6 +508,11 @@ def main():
         cfg["N_total"] = world * C5_SLAB_N
         extra["variants"] = {HEADLINE + "_kernel_only_rank0": res}
         extra["allgather_bytes_per_step"] = world * C5_SLAB_N * 4
+        tn = torch.tensor([ms_nccl], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+        extra["join"] = {"used": join_used, "us_per_step_fused": None if ms_fused is None else round(ms / args.steps * 1e3, 3),
+                         "us_per_step_nccl": round(float(tn[0]) / args.steps * 1e3, 3),
+                         "us_kernel_only_rank0": res["us_per_call"]}
         roof_alg, roof_us = alg, res["us_per_call"]
         roof_kernel = "panel_kernel<16,false,true,16>"
         scaling = "weak"

@@ -25,7 +25,10 @@ namespace {
 constexpr int kAspThreads = 128;
 constexpr int kAspTile = kAspThreads * 4;     // output columns per CTA
 constexpr int kAspChunk = 1024;               // rows compacted per pass
-constexpr int kAspStages = 16;             // rows in flight per warp
+#ifndef SPMV_ASP_STAGES
+#define SPMV_ASP_STAGES 16
+#endif
+constexpr int kAspStages = SPMV_ASP_STAGES; // rows in flight per warp
 
 __global__ void __launch_bounds__(kAspThreads)
 asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ x, const YDst yd,
@@ -36,7 +39,7 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
     __shared__ float xs_s[kAspChunk];
     __shared__ int wcnt[kAspThreads / 32];
     __shared__ int last_flag;
-    __shared__ __align__(16) float4 ring_all[(kAspThreads / 32) * kAspStages * 32];
+    extern __shared__ __align__(16) float4 ring_all[];    // (kAspThreads / 32) * kAspStages * 32
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x, split = blockIdx.y;
@@ -122,7 +125,13 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
 int launch_asp(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st)
 {
     if (p->N == 0) return SPMV_OK;
-    asp_kernel<<<p->grid, kAspThreads, 0, st>>>(p->asp.A, (long long)p->asp.ld, d_x, yd, p->partial, p->tickets,
+    const int smem = (kAspThreads / 32) * kAspStages * 32 * (int)sizeof(float4);
+    static int smem_set[16] = {0};
+    if (smem > 48 * 1024 && p->device >= 0 && p->device < 16 && smem_set[p->device] < smem) {
+        SPMV_CUDA(cudaFuncSetAttribute(asp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set[p->device] = smem;
+    }
+    asp_kernel<<<p->grid, kAspThreads, smem, st>>>(p->asp.A, (long long)p->asp.ld, d_x, yd, p->partial, p->tickets,
                                                (int)p->M, (int)p->N, p->asp.rows_per_split, p->row_splits);
     SPMV_CUDA(cudaGetLastError());
     return SPMV_OK;
@@ -134,7 +143,7 @@ int launch_asp(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st)
 int configure_asp(spmv_plan *p, const spmv_options_t *o)
 {
     p->block = kAspThreads;
-    p->smem = 0;
+    p->smem = (kAspThreads / 32) * kAspStages * 32 * (int)sizeof(float4);
     p->tile_width = kAspTile;
     p->col_tiles = (int)((p->N + kAspTile - 1) / kAspTile);
     p->asp.tile_cols = kAspTile;

@@ -64,9 +64,10 @@ template <> struct ColIdx<16> {
 //                         [slot info][multi-row mode: per-lane (x, row slot) ring]
 constexpr int kListCap = 128;              // rows a warp can take from one metadata batch
 constexpr int kMetaBatch = 8;              // 32-row blocks of metadata fetched together
-template <int IDXB, int kStages> __host__ __device__ constexpr int warp_smem_bytes(int W)
+template <int IDXB, int kStages, bool MR> __host__ __device__ constexpr int warp_smem_bytes(int W)
 {
-    return W * 4 + kStages * 32 * 16 + kStages * 32 * (IDXB == 8 ? 4 : 8) + kListCap * 16 + kStages * 8 + kStages * 32 * 8;
+    return W * 4 + kStages * 32 * 16 + kStages * 32 * (IDXB == 8 ? 4 : 8) + kListCap * 16 + kStages * 8 +
+           (MR ? kStages * 32 * 8 : 0);
 }
 
 // Balanced flat decomposition.  The (slab, row) pairs, slab-major, form one sequence of
@@ -94,7 +95,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_warps = blockDim.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes<IDXB, kStages>(W);
+    unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes<IDXB, kStages, MR>(W);
     float *acc = reinterpret_cast<float *>(wbase);
     float4 *ring_v = reinterpret_cast<float4 *>(wbase + (size_t)W * 4);
     IVec *ring_i = reinterpret_cast<IVec *>(wbase + (size_t)W * 4 + kStages * 32 * 16);
@@ -244,11 +245,12 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         // a CTA end up with equal shares whatever the piece length.
         // Metadata is fetched kMetaBatch blocks at a time, one batch ahead of its use, so its
         // latency is paid once per 128 rows and overlaps the previous batch's streaming.
-        // Long pieces: warp w owns blocks w, w + n_warps, ... outright (no redundant metadata
-        // loads, statistically balanced).  Short pieces: every warp scans every block and keeps
-        // the active rows whose rank is w modulo the warp count (exact balance).
+        // Pieces with at least one block per warp: warp w owns blocks w, w + n_warps, ... outright
+        // (no redundant metadata loads, one metadata latency per 256 of its rows, statistically
+        // balanced).  Shorter pieces: every warp scans every block (a single batch) and keeps the
+        // active rows whose rank is w modulo the warp count (exact balance).
         const int blk_a = row_a >> 5, blk_b = (row_b + 31) >> 5;
-        const bool by_block = (blk_b - blk_a) >= 4 * n_warps;
+        const bool by_block = (blk_b - blk_a) >= n_warps;
         const int bstep = by_block ? n_warps : 1;
         const int bfirst = blk_a + (by_block ? warp : 0);
         int rank_base = 0;
@@ -300,7 +302,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         const int n_pieces = (int)(c_hi - c_lo + 1);
         const int col0 = slab * W;
         const int n_valid = min(W, N - col0);
-        const int wstride = warp_smem_bytes<IDXB, kStages>(W) / 4;
+        const int wstride = warp_smem_bytes<IDXB, kStages, MR>(W) / 4;
         const float *acc0 = reinterpret_cast<const float *>(smem_raw);
         float *dst = partial + ((size_t)blockIdx.x * kmax + piece) * W;
         for (int c = tid; c < n_valid; c += blockDim.x) {
@@ -366,19 +368,22 @@ int launch_panel(spmv_plan *p, const float *d_x, const YDst &d_y, cudaStream_t s
 // Geometry: a 1-D grid of G CTAs over the flat (slab, row) sequence, one resident wave.
 // Every CTA pays a few microseconds of serial latency (metadata, first chunks, cross-warp and
 // cross-piece sums), so more than one wave only adds latency (measured, profiles/r01_notes.md);
-// 8-warp CTAs, as many per SM as shared memory allows (at most 4: ~24-32 warps per SM).
+// 8-warp CTAs, two per SM where shared memory allows (a third adds more fixed cost than it hides:
+// 444 CTAs 21.2 us vs 296 CTAs 16.4 us on the 4096x4096 / 50 % case).
 int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o)
 {
     DevPanel &d = p->panel;
     d.slab_cols = h.slab_cols; d.index_bits = h.index_bits; d.slabs = h.slabs;
     d.row_blocks = h.row_blocks; d.tiled = h.tiled;
-    // short segments (fewer than ~20 groups on average): pack several rows into one chunk
+    // short segments (fewer than 12 groups on average, i.e. chunks less than 3/8 full): pack
+    // several rows into one chunk
     const double segs = std::max<double>(1.0, (double)h.nonempty_segments);
-    d.multirow = (double)h.groups / segs < 20.0;
+    d.multirow = (double)h.groups / segs < 12.0;
     if (o && o->chunk_mode == 1) d.multirow = false;
     if (o && o->chunk_mode == 2) d.multirow = true;
     const int smem_cap = p->max_smem_optin > 0 ? p->max_smem_optin : 227 * 1024;
-    const int per_warp = h.index_bits == 8 ? warp_smem_bytes<8, kRingStages>(h.slab_cols) : warp_smem_bytes<16, kRingStages>(h.slab_cols);
+    const int per_warp = d.multirow ? (h.index_bits == 8 ? warp_smem_bytes<8, kRingStages, true>(h.slab_cols) : warp_smem_bytes<16, kRingStages, true>(h.slab_cols))
+                                    : (h.index_bits == 8 ? warp_smem_bytes<8, kRingStages, false>(h.slab_cols) : warp_smem_bytes<16, kRingStages, false>(h.slab_cols));
     int warps = 8;
     if (o && o->warps_per_col > 0) {
         warps = 1;
@@ -396,8 +401,11 @@ int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o)
 
     const int slabs = std::max(1, h.slabs);
     const int64_t M = std::max<int64_t>(1, h.M);
-    const int resident = std::max(1, std::min(std::min(4, 2048 / p->block), (228 * 1024) / (p->smem + 1024)));
+    const int resident = std::max(1, std::min(std::min(2, 2048 / p->block), (228 * 1024) / (p->smem + 1024)));
     int64_t G = (int64_t)p->sm_count * resident;
+    // a whole number of CTAs per slab when that costs under 10 % of the grid: no piece crosses a
+    // slab boundary, so no CTA pays the per-piece overhead twice (288 vs 296 CTAs: 11.9 vs 13.8 us)
+    if (G >= slabs && (G / slabs) * slabs * 10 >= G * 9) G = (G / slabs) * slabs;
     if (o && o->row_splits > 0) G = (int64_t)slabs * o->row_splits;       // forced: row_splits CTAs per slab
     const int64_t T = (int64_t)slabs * M;
     G = std::max<int64_t>(1, std::min<int64_t>(G, (T + 31) / 32));         // at least 32 rows per CTA
