@@ -311,3 +311,25 @@ def test_smoke_entry(S):
     sys.path.insert(0, root)
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_run_scatter_into_several_buffers(S):
+    """spmv_run_scatter on one GPU: the slice lands at `offset` in every destination buffer
+    (what the column-sharded path does with its peers' buffers)."""
+    import torch
+    A = ob.gen_matrix(512, 1024, 0.7, 61)
+    x = ob.gen_vector(512, 0.5, 62)
+    dx = torch.from_numpy(x).cuda()
+    for v in VARIANTS:
+        with S.Plan.from_dense(v, A[:, 256:768]) as p:          # a 512-column slab of a 1024-column y
+            ref = p.run_host(x)
+            bufs = [torch.full((1024,), -7.0, device="cuda") for _ in range(3)]
+            p.run_scatter(dx, [b.data_ptr() for b in bufs], 256)
+            torch.cuda.synchronize()
+            for b in bufs:
+                h = b.cpu().numpy()
+                assert h[256:768].tobytes() == ref.tobytes(), v
+                assert np.all(h[:256] == -7.0) and np.all(h[768:] == -7.0), v
+    with S.Plan.from_dense("wsp", A) as p:
+        with pytest.raises(S.SpmvError):
+            p.run_scatter(dx, [bufs[0].data_ptr()], 2)          # offset not a multiple of 4
