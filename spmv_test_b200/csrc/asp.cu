@@ -22,7 +22,10 @@ namespace spmv {
 
 namespace {
 
-constexpr int kAspThreads = 128;
+#ifndef SPMV_ASP_THREADS
+#define SPMV_ASP_THREADS 128
+#endif
+constexpr int kAspThreads = SPMV_ASP_THREADS;
 constexpr int kAspTile = kAspThreads * 4;     // output columns per CTA
 constexpr int kAspChunk = 1024;               // rows compacted per pass
 #ifndef SPMV_ASP_STAGES
