@@ -202,7 +202,8 @@ SPMV_API int spmv_partition_columns(int64_t N, int parts, int64_t align, const i
  * Packs like spmv_plan_create_dense / _csc would, but hands the host image of the device
  * format back instead of uploading it: the CPU test-suite decodes it to check the packers
  * (group padding, offsets, column ids) without a GPU.  Not a compute path.
- *   SPMV_WSP        vals[4*groups], idx (u16|u32)[4*groups], off = colptr[N+1]
+ *   SPMV_WSP        vals[4*(groups+1)], idx (u16|u32)[4*(groups+1)], off = colptr[panels*N+1]
+ *                   (slabs = row panels, slab_cols = rows per panel; one list per (panel, column))
  *   SPMV_AWSP       vals, idx (u8|u16)[4*groups], off[slabs*(M+1)]
  *   SPMV_TCSR       vals, idx, off = tile_off[slabs*(row_blocks+1)], rel[slabs*row_blocks*32]
  */

@@ -346,7 +346,8 @@ int spmv_plan_traffic(const spmv_plan_t *p, const float *x, double *alg_bytes, d
     if (p->variant == SPMV_WSP) {
         touched = p->nnz;
         alg = 8.0 * touched + 4.0 * (N + 1) + vec;
-        phys = (double)p->fmt_groups * (16.0 + 4.0 * p->wsp.index_bits / 8.0) + 4.0 * (N + 1) + vec;
+        phys = (double)p->fmt_groups * (16.0 + 4.0 * p->wsp.index_bits / 8.0) + 4.0 * (N * p->wsp.panels + 1) + vec +
+               (p->wsp.panels > 1 ? 2.0 * 4.0 * N * p->wsp.panels : 0.0);
     } else if (p->variant == SPMV_ASP) {
         int64_t mnz = 0;
         for (int64_t j = 0; j < p->M; j++) mnz += (x[j] != 0.0f);

@@ -13,11 +13,18 @@ namespace spmv {
 //   colptr uint32 [N+1]              first group of each column (sentinel included)
 // A column is padded to a multiple of 4 with (value 0, index M); the kernels keep one zero
 // at x[M] so a pad contributes an exact 0 regardless of x.
+// Row panels (tall matrices whose x does not fit shared memory, e.g. config 5): the rows are
+// cut into `panels` panels of `panel_rows` rows, every (panel, column) pair has its own list
+// (panel-major: colptr[p*N + c]), row ids are panel-local 16-bit and the pad index is
+// `panel_rows`; a CTA works inside one panel with that panel's slice of x in shared memory, and
+// the per-panel sums are added in panel order.
 // ------------------------------------------------------------------------------------------
 struct HostWsp {
     int64_t M = 0, N = 0, nnz = 0, groups = 0;
     int index_bits = 16;
-    std::vector<uint32_t> colptr;  // N+1
+    int panels = 1;
+    int64_t panel_rows = 0;        // rows per panel (== M when panels == 1)
+    std::vector<uint32_t> colptr;  // panels*N+1
     std::vector<float> vals;       // 4*groups
     std::vector<uint16_t> idx16;   // 4*groups (index_bits == 16)
     std::vector<uint32_t> idx32;   // 4*groups (index_bits == 32)

@@ -16,36 +16,39 @@
 namespace spmv {
 
 // ---------------------------------------------------------------------------- WSP ---------
-static void wsp_finish_layout(HostWsp &w, const std::vector<int64_t> &col_nnz)
+// Lists are indexed by l = panel * N + column.
+static void wsp_finish_layout(HostWsp &w, const std::vector<int64_t> &list_nnz)
 {
-    const int64_t N = w.N;
-    w.colptr.resize(N + 1);
+    const int64_t L = (int64_t)w.panels * w.N;
+    w.colptr.resize(L + 1);
     int64_t g = 0, mx = 0;
-    for (int64_t i = 0; i < N; i++) {
+    for (int64_t i = 0; i < L; i++) {
         w.colptr[i] = (uint32_t)g;
-        int64_t cg = (col_nnz[i] + 3) / 4;
+        int64_t cg = (list_nnz[i] + 3) / 4;
         mx = std::max(mx, cg);
         g += cg;
     }
-    w.colptr[N] = (uint32_t)g;
+    w.colptr[L] = (uint32_t)g;
     w.groups = g;
     w.max_col_groups = mx;
+    const uint32_t pad = (uint32_t)w.panel_rows;
     // one spare pad group at the end: the ring kernel may address group `groups` (never uses it)
     w.vals.assign((size_t)(g + 1) * 4, 0.0f);
-    if (w.index_bits == 16) w.idx16.assign((size_t)(g + 1) * 4, (uint16_t)w.M);
-    else w.idx32.assign((size_t)(g + 1) * 4, (uint32_t)w.M);
+    if (w.index_bits == 16) w.idx16.assign((size_t)(g + 1) * 4, (uint16_t)pad);
+    else w.idx32.assign((size_t)(g + 1) * 4, pad);
 }
 
-// Inside a column the order of the entries is free (any fixed order is deterministic), so it is
+// Inside a list the order of the entries is free (any fixed order is deterministic), so it is
 // chosen for the kernel's shared-memory gathers of x: within a chunk of 32 groups the 32 lanes
 // gather element e of their group in one instruction, and the entries are dealt so that those
-// row ids fall into distinct banks (row mod 32) as far as the column allows.
+// row ids fall into distinct banks (row mod 32) as far as the list allows.
 template <class IdxT> static void wsp_bank_deal(HostWsp &w, std::vector<IdxT> &idx)
 {
     std::vector<int> bucket[32];
     std::vector<IdxT> oi(128);
     std::vector<float> ov(128);
-    for (int64_t c = 0; c < w.N; c++)
+    const int64_t L = (int64_t)w.panels * w.N;
+    for (int64_t c = 0; c < L; c++)
         for (int64_t c0 = w.colptr[c]; c0 < w.colptr[c + 1]; c0 += 32) {
             const int lanes = (int)std::min<int64_t>(32, w.colptr[c + 1] - c0);
             const size_t first = (size_t)c0 * 4;
@@ -79,31 +82,54 @@ static void wsp_bank_order(HostWsp &w)
     if (w.index_bits == 16) wsp_bank_deal(w, w.idx16); else wsp_bank_deal(w, w.idx32);
 }
 
+// Row panels: when x (M floats) does not fit shared memory next to the ring but the lists
+// stay long enough after the cut (>= 32 non-zeros per (panel, column) on average), cut the rows
+// into panels of 12288 (48 KB of x + 48 KB of ring per CTA: two CTAs per SM).
+static void wsp_choose_panels(HostWsp &w, int64_t nnz, int index_bits_opt)
+{
+    constexpr int64_t kPanelRows = 12288;
+    w.panels = 1; w.panel_rows = w.M;
+    const bool x_fits = ((size_t)w.M + 4) * sizeof(float) <= 96 * 1024;
+    if (!x_fits && index_bits_opt != 32 && w.N > 0) {
+        const int64_t P = (w.M + kPanelRows - 1) / kPanelRows;
+        if ((double)nnz / ((double)P * (double)w.N) >= 32.0) { w.panels = (int)P; w.panel_rows = kPanelRows; }
+    }
+    w.index_bits = index_bits_opt ? index_bits_opt : (w.panel_rows < 65536 ? 16 : 32);
+}
+
 int pack_wsp_dense(int64_t M, int64_t N, const float *A, int64_t lda, int index_bits, HostWsp &w)
 {
     w.M = M; w.N = N;
-    w.index_bits = index_bits ? index_bits : (M < 65536 ? 16 : 32);
-    if (w.index_bits == 16 && M >= 65536) return SPMV_ERR_ARG;
-    std::vector<int64_t> cnt((size_t)N, 0);
-    for (int64_t j = 0; j < M; j++) {            // row-major sweep: rows arrive in ascending order
-        const float *row = A + j * lda;
-        for (int64_t i = 0; i < N; i++) cnt[i] += (row[i] != 0.0f);
-    }
+    std::vector<int64_t> col_cnt((size_t)N, 0);
     int64_t nnz = 0;
-    for (int64_t i = 0; i < N; i++) nnz += cnt[i];
-    w.nnz = nnz;
-    if ((nnz + 3 * N) / 4 >= (int64_t)UINT32_MAX) return SPMV_ERR_UNSUPPORTED;
-    wsp_finish_layout(w, cnt);
-    std::vector<int64_t> cur((size_t)N);
-    for (int64_t i = 0; i < N; i++) cur[i] = (int64_t)w.colptr[i] * 4;
     for (int64_t j = 0; j < M; j++) {
         const float *row = A + j * lda;
+        for (int64_t i = 0; i < N; i++) nnz += (row[i] != 0.0f);
+    }
+    w.nnz = nnz;
+    wsp_choose_panels(w, nnz, index_bits);
+    if (w.index_bits == 16 && w.panel_rows >= 65536) return SPMV_ERR_ARG;
+    std::vector<int64_t> cnt((size_t)w.panels * N, 0);
+    for (int64_t j = 0; j < M; j++) {            // row-major sweep: rows arrive in ascending order
+        const float *row = A + j * lda;
+        int64_t *c = cnt.data() + (w.panels > 1 ? j / w.panel_rows : 0) * N;
+        for (int64_t i = 0; i < N; i++) c[i] += (row[i] != 0.0f);
+    }
+    if ((nnz + 3 * (int64_t)cnt.size()) / 4 >= (int64_t)UINT32_MAX) return SPMV_ERR_UNSUPPORTED;
+    wsp_finish_layout(w, cnt);
+    std::vector<int64_t> cur(cnt.size());
+    for (size_t i = 0; i < cnt.size(); i++) cur[i] = (int64_t)w.colptr[i] * 4;
+    for (int64_t j = 0; j < M; j++) {
+        const float *row = A + j * lda;
+        const int64_t pj = w.panels > 1 ? j / w.panel_rows : 0;
+        const int64_t local = j - pj * (w.panels > 1 ? w.panel_rows : 0);
+        int64_t *c = cur.data() + pj * N;
         for (int64_t i = 0; i < N; i++) {
             float v = row[i];
             if (v != 0.0f) {
-                int64_t p = cur[i]++;
+                int64_t p = c[i]++;
                 w.vals[p] = v;
-                if (w.index_bits == 16) w.idx16[p] = (uint16_t)j; else w.idx32[p] = (uint32_t)j;
+                if (w.index_bits == 16) w.idx16[p] = (uint16_t)local; else w.idx32[p] = (uint32_t)local;
             }
         }
     }
@@ -115,30 +141,31 @@ int pack_wsp_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *ro
                  const float *values, int index_bits, HostWsp &w)
 {
     w.M = M; w.N = N;
-    w.index_bits = index_bits ? index_bits : (M < 65536 ? 16 : 32);
-    if (w.index_bits == 16 && M >= 65536) return SPMV_ERR_ARG;
-    std::vector<int64_t> cnt((size_t)N, 0);
     int64_t nnz = 0;
-    for (int64_t i = 0; i < N; i++) {
-        int64_t c = 0;
-        for (int64_t k = col_ptr[i]; k < col_ptr[i + 1]; k++) {
-            if (row_idx[k] < 0 || row_idx[k] >= M) return SPMV_ERR_ARG;
-            c += (values[k] != 0.0f);
-        }
-        cnt[i] = c; nnz += c;
+    for (int64_t k = col_ptr[0]; k < col_ptr[N]; k++) {
+        if (row_idx[k] < 0 || row_idx[k] >= M) return SPMV_ERR_ARG;
+        nnz += (values[k] != 0.0f);
     }
     w.nnz = nnz;
-    if ((nnz + 3 * N) / 4 >= (int64_t)UINT32_MAX) return SPMV_ERR_UNSUPPORTED;
+    wsp_choose_panels(w, nnz, index_bits);
+    if (w.index_bits == 16 && w.panel_rows >= 65536) return SPMV_ERR_ARG;
+    std::vector<int64_t> cnt((size_t)w.panels * N, 0);
+    for (int64_t i = 0; i < N; i++)
+        for (int64_t k = col_ptr[i]; k < col_ptr[i + 1]; k++)
+            if (values[k] != 0.0f) cnt[(size_t)(w.panels > 1 ? row_idx[k] / w.panel_rows : 0) * N + i]++;
+    if ((nnz + 3 * (int64_t)cnt.size()) / 4 >= (int64_t)UINT32_MAX) return SPMV_ERR_UNSUPPORTED;
     wsp_finish_layout(w, cnt);
-    for (int64_t i = 0; i < N; i++) {
-        int64_t p = (int64_t)w.colptr[i] * 4;
+    std::vector<int64_t> cur(cnt.size());
+    for (size_t i = 0; i < cnt.size(); i++) cur[i] = (int64_t)w.colptr[i] * 4;
+    for (int64_t i = 0; i < N; i++)
         for (int64_t k = col_ptr[i]; k < col_ptr[i + 1]; k++) {
             if (values[k] == 0.0f) continue;
+            const int64_t pj = w.panels > 1 ? row_idx[k] / w.panel_rows : 0;
+            const int64_t local = row_idx[k] - pj * (w.panels > 1 ? w.panel_rows : 0);
+            const int64_t p = cur[(size_t)pj * N + i]++;
             w.vals[p] = values[k];
-            if (w.index_bits == 16) w.idx16[p] = (uint16_t)row_idx[k]; else w.idx32[p] = (uint32_t)row_idx[k];
-            p++;
+            if (w.index_bits == 16) w.idx16[p] = (uint16_t)local; else w.idx32[p] = (uint32_t)local;
         }
-    }
     wsp_bank_order(w);
     return SPMV_OK;
 }
@@ -553,6 +580,7 @@ template <class T> T *dup_vec(const std::vector<T> &v)
 void dump_wsp(const spmv::HostWsp &w, spmv_packed_dump_t *o)
 {
     o->variant = SPMV_WSP; o->index_bits = w.index_bits; o->M = w.M; o->N = w.N; o->nnz = w.nnz; o->groups = w.groups;
+    o->slabs = w.panels; o->slab_cols = (int32_t)w.panel_rows;      // wsp: row panels, rows per panel
     o->vals = dup_vec(w.vals); o->n_vals = (int64_t)w.vals.size();
     if (w.index_bits == 16) { o->idx = dup_vec(w.idx16); o->idx_bytes = (int64_t)w.idx16.size() * 2; }
     else { o->idx = dup_vec(w.idx32); o->idx_bytes = (int64_t)w.idx32.size() * 4; }

@@ -37,6 +37,7 @@ struct DevWsp {
     int index_bits = 16;
     int warps_per_col = 1;
     bool x_in_smem = true;
+    int panels = 1;             // row panels (tall matrices)
 };
 
 struct DevAsp {

@@ -164,12 +164,19 @@ template <typename IdxVec>
 __global__ void __launch_bounds__(kRingWarps * 32)
 wsp_ring_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
                 const uint32_t *__restrict__ colptr, const int32_t *__restrict__ cols, int ncols,
-                const float *__restrict__ x, const YDst yd, uint32_t M, int x_bulk_ok, int xs_bytes)
+                const float *__restrict__ x, const YDst yd, uint32_t M_total, int x_bulk_ok, int xs_bytes,
+                uint32_t panel_rows, int n_total, float *__restrict__ partial)
 {
     extern __shared__ __align__(16) unsigned char wsm[];
     __shared__ __align__(8) uint64_t bar;
     float *xs = reinterpret_cast<float *>(wsm);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // row panel of this CTA (blockIdx.y): its slice of x goes to shared memory, its lists start at
+    // colptr[panel * N]; rows past the slice (last panel) and the pad slot read as zero
+    const uint32_t panel = blockIdx.y;
+    const uint32_t M = min(panel_rows, M_total - panel * panel_rows);
+    x += (size_t)panel * panel_rows;
+    colptr += (size_t)panel * n_total;
     float4 *ring_v = reinterpret_cast<float4 *>(wsm + xs_bytes) + warp * kRingStages * 32;
     IdxVec *ring_i = reinterpret_cast<IdxVec *>(wsm + xs_bytes + kRingWarps * kRingStages * 32 * 16) + warp * kRingStages * 32;
 
@@ -189,23 +196,38 @@ wsp_ring_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
     } else {
         for (uint32_t j = tid; j < M; j += blockDim.x) xs[j] = x[j];
     }
-    if (tid < 4) xs[M + tid] = 0.0f;                      // the pad slot
+    for (uint32_t j = M + tid; j < panel_rows + 4; j += blockDim.x) xs[j] = 0.0f;   // tail of the last panel + pad slot
 
     // ---- flat iterator over (column, chunk) ---------------------------------------------------------
+    // This warp's columns are positions kbase, kbase + nwarps, ... of the column list.  Their
+    // (column id, first group, end group) are fetched 32 at a time — lane l holds the l-th
+    // upcoming column — one batch ahead of use, so even one-chunk columns keep the ring full.
     const int nwarps = gridDim.x * kRingWarps;
-    int k = blockIdx.x * kRingWarps + warp;               // position in the column list
-    uint32_t g = 0, gend = 0; int ccol = -1; bool live = true;
-    uint32_t n0 = 0, n1 = 0; int ncol = -1;               // next column, prefetched
-    auto fetch_col = [&](int kk) {
-        if (kk < ncols) { ncol = cols ? cols[kk] : kk; n0 = __ldg(colptr + ncol); n1 = __ldg(colptr + ncol + 1); }
-        else ncol = -1;
+    const int kbase = blockIdx.x * kRingWarps + warp;
+    int bc = -1, nc = -1; uint32_t b0 = 0, b1 = 0, n0 = 0, n1 = 0;   // current / next batch (per lane)
+    int jb = 0;                                            // index of the next column inside the current batch
+    int batch0 = 0;                                        // list position (in this warp's sequence) of the next batch
+    auto fetch_batch = [&](int j0) {
+        const long long kk = (long long)kbase + (long long)(j0 + lane) * nwarps;
+        nc = -1; n0 = 0; n1 = 0;
+        if (kk < ncols) { nc = cols ? cols[kk] : (int)kk; n0 = __ldg(colptr + nc); n1 = __ldg(colptr + nc + 1); }
     };
-    fetch_col(k);
+    fetch_batch(0);
+    bc = nc; b0 = n0; b1 = n1;
+    batch0 = 32;
+    fetch_batch(batch0);
+    uint32_t g = 0, gend = 0; int ccol = -1; bool live = true;
     auto next_col = [&]() {
-        if (ncol < 0) { live = false; return; }
-        ccol = ncol; g = n0; gend = n1;
-        k += nwarps;
-        fetch_col(k);
+        if (jb == 32) {                                    // promote the prefetched batch
+            bc = nc; b0 = n0; b1 = n1; jb = 0;
+            batch0 += 32;
+            fetch_batch(batch0);
+        }
+        ccol = __shfl_sync(kFull, bc, jb);
+        g = __shfl_sync(kFull, b0, jb);
+        gend = __shfl_sync(kFull, b1, jb);
+        jb++;
+        if (ccol < 0) live = false;
     };
     next_col();
 
@@ -245,7 +267,10 @@ wsp_ring_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
                 a2 = fmaf(v.z, xs[i[2]], a2); a3 = fmaf(v.w, xs[i[3]], a3);
                 if (fin[s] >= 0) {
                     const float t = warp_sum((a0 + a1) + (a2 + a3));
-                    if (lane == 0) y_store(yd, fin[s], t);
+                    if (lane == 0) {
+                        if (gridDim.y == 1) y_store(yd, fin[s], t);
+                        else partial[(size_t)panel * n_total + fin[s]] = t;
+                    }
                     a0 = a1 = a2 = a3 = 0.f;
                 }
             }
@@ -253,6 +278,17 @@ wsp_ring_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
         }
     }
     cp_async_wait<0>();
+}
+
+// y = sum over the row panels, in panel order
+__global__ void __launch_bounds__(256)
+wsp_combine_kernel(const float *__restrict__ partial, int panels, int n, const YDst yd)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    float s = partial[c];
+    for (int p = 1; p < panels; p++) s += partial[(size_t)p * n + c];
+    y_store(yd, c, s);
 }
 
 struct Bin { int T; std::vector<int32_t> cols; };
@@ -266,6 +302,9 @@ struct WspBinDev { int T; int32_t *cols; int ncols; int grid; bool ring; int sme
 
 struct WspState {            // hangs off the plan through plan->wsp_state
     std::vector<WspBinDev> bins;
+    int panels = 1;
+    int64_t panel_rows = 0;
+    float *partial = nullptr;    // [panels][N] when panels > 1
 };
 
 template <typename IdxVec, int T, bool XS>
@@ -310,10 +349,15 @@ static int launch_ring(const spmv_plan *p, const WspBinDev &b, const float *x, c
         SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, b.smem));
         smem_set[p->device] = b.smem;
     }
-    k<<<b.grid, kRingWarps * 32, b.smem, st>>>(reinterpret_cast<const float4 *>(p->wsp.vals),
-                                              reinterpret_cast<const IdxVec *>(p->wsp.idx), p->wsp.colptr, b.cols,
-                                              b.ncols, x, y, (uint32_t)p->M, ok, p->smem);
+    const WspState *ws = reinterpret_cast<const WspState *>(p->wsp_state);
+    k<<<dim3(b.grid, ws->panels), kRingWarps * 32, b.smem, st>>>(
+        reinterpret_cast<const float4 *>(p->wsp.vals), reinterpret_cast<const IdxVec *>(p->wsp.idx), p->wsp.colptr, b.cols,
+        b.ncols, x, y, (uint32_t)p->M, ok, p->smem, (uint32_t)ws->panel_rows, (int)p->N, ws->partial);
     SPMV_CUDA(cudaGetLastError());
+    if (ws->panels > 1) {
+        wsp_combine_kernel<<<(unsigned)((p->N + 255) / 256), 256, 0, st>>>(ws->partial, ws->panels, (int)p->N, y);
+        SPMV_CUDA(cudaGetLastError());
+    }
     return SPMV_OK;
 }
 
@@ -349,8 +393,16 @@ int configure_wsp(spmv_plan *p, const HostWsp &w, const spmv_options_t *o)
     WspState *s = new WspState();
     p->wsp_state = s;
     p->wsp.index_bits = w.index_bits;
-    // x in shared memory when it (plus the pad slot) fits comfortably next to several CTAs/SM
-    const size_t xbytes = ((size_t)w.M + 4) * sizeof(float);
+    s->panels = w.panels;
+    p->wsp.panels = w.panels;
+    s->panel_rows = w.panels > 1 ? w.panel_rows : w.M;
+    if (w.panels > 1) {
+        SPMV_CUDA(cudaMalloc(&s->partial, (size_t)w.panels * std::max<int64_t>(w.N, 1) * sizeof(float)));
+        p->scratch_bytes += (int64_t)w.panels * w.N * 4;
+    }
+    // x (one row panel of it) in shared memory when it (plus the pad slot) fits comfortably next
+    // to several CTAs/SM
+    const size_t xbytes = ((size_t)s->panel_rows + 4) * sizeof(float);
     p->wsp.x_in_smem = xbytes <= 96 * 1024 && w.index_bits == 16;
     if (w.index_bits == 32 && xbytes <= 96 * 1024) p->wsp.x_in_smem = true;
     p->smem = p->wsp.x_in_smem ? (int)((xbytes + 15) & ~(size_t)15) : 0;
@@ -364,15 +416,15 @@ int configure_wsp(spmv_plan *p, const HostWsp &w, const spmv_options_t *o)
         return std::min(256, std::max(4, t));
     };
     int64_t gmin = INT64_MAX, gmax = 0;
-    for (int64_t i = 0; i < N; i++) {
+    for (int64_t i = 0; i < N * w.panels; i++) {
         int64_t g = (int64_t)w.colptr[i + 1] - w.colptr[i];
         gmin = std::min(gmin, g); gmax = std::max(gmax, g);
     }
-    const int64_t gmean = N ? (w.groups + N - 1) / N : 0;
+    const int64_t gmean = N ? (w.groups + N * w.panels - 1) / (N * w.panels) : 0;
     int forced = 0;
     if (o && o->warps_per_col > 0) forced = std::min(256, 32 * pow2_ceil(o->warps_per_col));
     std::vector<Bin> bins;
-    if (forced || N == 0 || team_for(gmax) <= 2 * team_for(std::max<int64_t>(gmin, 1))) {
+    if (forced || N == 0 || w.panels > 1 || team_for(gmax) <= 2 * team_for(std::max<int64_t>(gmin, 1))) {
         bins.push_back({forced ? forced : team_for(gmean), {}});           // one bin: all columns, no list
     } else {
         const int Ts[7] = {4, 8, 16, 32, 64, 128, 256};
@@ -401,17 +453,17 @@ int configure_wsp(spmv_plan *p, const HostWsp &w, const spmv_options_t *o)
         const int64_t need = ((int64_t)d.ncols + teams_per_cta - 1) / teams_per_cta;
         d.grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)p->sm_count * ctas_per_sm));
         d.ring = false; d.smem = 0;
-        if (p->wsp.x_in_smem && b.T >= 32 && !(o && o->warps_per_col > 0)) {
+        if (p->wsp.x_in_smem && (b.T >= 32 || w.panels > 1) && !(o && o->warps_per_col > 0 && w.panels == 1)) {
             // long columns: warp per column through the cp.async ring
             d.ring = true;
             d.smem = p->smem + kRingWarps * kRingStages * 32 * (16 + (w.index_bits == 16 ? 8 : 16));
             const int resident = std::max(1, std::min(8, (220 * 1024) / (d.smem + 1024)));
             const int64_t want = ((int64_t)d.ncols + kRingWarps - 1) / kRingWarps;
-            d.grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * resident));
+            d.grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, ((int64_t)p->sm_count * resident + w.panels - 1) / w.panels));
         }
         s->bins.push_back(d);
     }
-    p->kernels_per_run = (int)s->bins.size();
+    p->kernels_per_run = (int)s->bins.size() + (w.panels > 1 ? 1 : 0);
     p->grid = dim3(s->bins.empty() ? 1 : s->bins[0].grid, 1, 1);
     p->wsp.warps_per_col = s->bins.empty() ? 0 : std::max(1, s->bins[0].T / 32);
     p->wsp_team = s->bins.empty() ? 0 : s->bins[0].T;
@@ -424,6 +476,8 @@ int clone_wsp_state(const spmv_plan *src, spmv_plan *dst)
     WspState *d = new WspState();
     dst->wsp_state = d;
     if (!s) return SPMV_OK;
+    d->panels = s->panels; d->panel_rows = s->panel_rows;
+    if (s->partial) SPMV_CUDA(cudaMalloc(&d->partial, (size_t)s->panels * std::max<int64_t>(src->N, 1) * sizeof(float)));
     for (const WspBinDev &b : s->bins) {
         WspBinDev nb = b;
         nb.cols = nullptr;
@@ -443,6 +497,7 @@ void destroy_wsp_state(spmv_plan *p)
     WspState *s = reinterpret_cast<WspState *>(p->wsp_state);
     if (!s) return;
     for (WspBinDev &b : s->bins) if (b.cols) cudaFree(b.cols);
+    if (s->partial) cudaFree(s->partial);
     delete s;
     p->wsp_state = nullptr;
 }

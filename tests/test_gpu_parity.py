@@ -333,3 +333,20 @@ def test_run_scatter_into_several_buffers(S):
     with S.Plan.from_dense("wsp", A) as p:
         with pytest.raises(S.SpmvError):
             p.run_scatter(dx, [bufs[0].data_ptr()], 2)          # offset not a multiple of 4
+
+
+def test_wsp_row_panels_tall(S):
+    """Tall matrix (x does not fit shared memory): wsp runs per 12288-row panel and adds the panel
+    sums in order; plus the 32-bit fallback when lists are short."""
+    for M, N, dens, seed in ((70000, 256, 0.01, 71), (40000, 96, 0.0005, 72)):
+        rng = np.random.default_rng(seed)
+        from spmv_test_b200 import synth
+        cp, ri, va = synth.bernoulli_csc(M, N, dens, seed)
+        x = ob.gen_vector(M, 0.5, seed + 1)
+        y_ref = ob.csc_gemv(N, cp, ri, va, x)
+        s = ob.csc_gemv(N, cp, ri, np.abs(va), np.abs(x)).astype(np.float64)
+        with S.Plan.from_csc("wsp", M, N, cp, ri, va) as p:
+            y = p.run_host(x)
+            assert p.run_host(x).tobytes() == y.tobytes()
+            err = np.abs(y.astype(np.float64) - y_ref)
+            assert float(np.max(err / (s + 1e-30))) <= 1e-5, (M, N)

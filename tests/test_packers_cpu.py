@@ -46,18 +46,22 @@ def decode_panel(d):
 
 
 def decode_wsp(d):
-    A = np.zeros((d.M + 1, d.N), np.float32)      # row M is the pad slot
+    panels, prow = d.slabs, d.slab_cols            # wsp dump: row panels, rows per panel (pad index)
+    A = np.zeros((max(d.M, panels * prow) + 1, d.N), np.float32)
     vals = d.vals.reshape(-1, 4)
     idx = d.idx.reshape(-1, 4).astype(np.int64)
-    assert vals.shape[0] == d.groups + 1 and np.all(vals[-1] == 0) and np.all(idx[-1] == d.M)   # spare pad group
-    for c in range(d.N):
-        g0, g1 = int(d.off[c]), int(d.off[c + 1])
-        v = vals[g0:g1].reshape(-1)
-        r = idx[g0:g1].reshape(-1)
-        assert np.all(r[v == 0] == d.M) and np.all(v[r == d.M] == 0)
-        real = v != 0
-        assert len(set(r[real])) == int(real.sum()), "a row occurs once per column"
-        A[r[real], c] = v[real]
+    assert vals.shape[0] == d.groups + 1 and np.all(vals[-1] == 0) and np.all(idx[-1] == prow)   # spare pad group
+    assert d.off.size == panels * d.N + 1
+    for p in range(panels):
+        for c in range(d.N):
+            g0, g1 = int(d.off[p * d.N + c]), int(d.off[p * d.N + c + 1])
+            v = vals[g0:g1].reshape(-1)
+            r = idx[g0:g1].reshape(-1)
+            assert np.all(r[v == 0] == prow) and np.all(v[r == prow] == 0)
+            real = v != 0
+            assert len(set(r[real])) == int(real.sum()), "a row occurs once per list"
+            assert np.all(r[real] < prow)
+            A[p * prow + r[real], c] = v[real]
     return A[:d.M]
 
 
@@ -135,3 +139,18 @@ def test_synthetic_generators():
     ln = np.diff(cp)
     assert 10 < ln.mean() < 24 and ln.max() > 20 * ln.mean()
     assert np.all(va != 0)
+
+
+def test_wsp_row_panels_for_tall_matrices():
+    """x of a tall matrix does not fit shared memory: rows are cut into 16384-row panels (12288 rows) with
+    panel-local 16-bit row ids when the lists stay long enough."""
+    import spmv_test_b200 as S
+    A = ob.gen_matrix(40000, 64, 0.99, 17)
+    d = S.pack_dump("wsp", A)
+    assert d.slabs == 4 and d.slab_cols == 12288 and d.index_bits == 16
+    assert np.array_equal(decode_wsp(d), A)
+    ptr, idx, val = ob.dense_to_csc(A)
+    e = S.pack_dump("wsp", csc=(ptr, idx, val), shape=A.shape)
+    assert d.vals.tobytes() == e.vals.tobytes() and d.idx.tobytes() == e.idx.tobytes() and d.off.tobytes() == e.off.tobytes()
+    thin = S.pack_dump("wsp", ob.gen_matrix(40000, 64, 0.9995, 18))      # lists too short: one panel, x through L2
+    assert thin.slabs == 1 and thin.slab_cols == 40000
