@@ -20,7 +20,11 @@
  *   - "d_" pointers are device pointers on the plan's device, "h_"/unprefixed
  *     pointers are host pointers.  stream is a cudaStream_t passed as void*.
  *   - spmv_run() is asynchronous, allocation-free and CUDA-graph capturable.
- *   - results are deterministic: no floating-point atomics anywhere.
+ *   - results are deterministic: no floating-point atomics anywhere; a plan reproduces its
+ *     results bit for bit (the work decomposition depends only on the shape and the device).
+ *   - a plan owns its split-reduction scratch: do not run ONE plan on two streams at the same
+ *     time (calls on one stream may overlap freely with other plans); spmv_plan_clone() gives an
+ *     independent copy.
  *   - there is no CPU fallback: if no CUDA device is usable the call fails.
  */
 #ifndef SPMV_B200_H
