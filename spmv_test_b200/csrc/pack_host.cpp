@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 
 #include "formats.hpp"
 #include "plan.hpp"
@@ -223,25 +224,29 @@ struct CscSource {
     }
 };
 
+// One slab's share of the panel format, built independently of the other slabs (offsets are
+// relative to the slab's first group); pack_panel concatenates the slabs.
+struct SlabOut {
+    std::vector<float> vals;
+    std::vector<uint8_t> idx8;
+    std::vector<uint16_t> idx16;
+    std::vector<uint32_t> off;      // per_slab entries, slab-relative
+    std::vector<uint16_t> rel;      // tiled only
+    int64_t groups = 0, nnz = 0, segs = 0;
+    int rc = SPMV_OK;
+};
+
+struct RowStats { std::vector<int32_t> nnz, groups, segs; };
+
 template <class Source>
-int pack_panel(int64_t M, int64_t N, bool tiled, int W, Source &src, HostPanel &P)
+void pack_slab(int s, int64_t M, bool tiled, int W, int index_bits, int row_blocks, Source &src, SlabOut &O, RowStats &st)
 {
-    if (W < kMinSlabCols || W > kMaxSlabCols || (W & (W - 1))) return SPMV_ERR_ARG;
-    P.M = M; P.N = N; P.tiled = tiled;
-    P.slab_cols = W;
-    P.index_bits = (W == 256) ? 8 : 16;
-    P.slabs = (int)((N + W - 1) / W);
-    P.row_blocks = (int)((M + kTileRows - 1) / kTileRows);
-    P.row_nnz.assign((size_t)M, 0);
-    P.row_groups.assign((size_t)M, 0);
-    P.row_segs.assign((size_t)M, 0);
-    P.nnz = 0; P.groups = 0; P.nonempty_segments = 0;
-    P.vals.clear(); P.idx8.clear(); P.idx16.clear(); P.rel.clear();
-    const int64_t per_slab = tiled ? (P.row_blocks + 1) : (M + 1);
-    P.off.assign((size_t)P.slabs * per_slab, 0);
-    if (tiled) P.rel.assign((size_t)P.slabs * P.row_blocks * kTileRows, 0);
-    std::vector<uint16_t> cols((size_t)W + 4);
-    std::vector<float> vals((size_t)W + 4);
+    const int64_t per_slab = tiled ? (row_blocks + 1) : (M + 1);
+    O.off.assign((size_t)per_slab, 0);
+    if (tiled) O.rel.assign((size_t)row_blocks * kTileRows, 0);
+    std::vector<uint16_t> cols((size_t)W + 4), ocols((size_t)W);
+    std::vector<float> vals((size_t)W + 4), ovals((size_t)W);
+    std::vector<int> bucket_of[32];
 
     // Inside a segment the order of the entries is free (every column occurs once per row), so
     // it is chosen for the kernel's shared-memory accumulators: within a chunk of 32 groups the
@@ -249,12 +254,9 @@ int pack_panel(int64_t M, int64_t N, bool tiled, int W, Source &src, HostPanel &
     // dealt so that those columns fall into distinct banks (column mod 32) as far as the row
     // allows.  Pads carry value 0 and the smallest column ABSENT from the segment: they add an
     // exact 0 to an accumulator no real entry of this row touches (n % 4 != 0 implies n < W).
-    std::vector<uint16_t> ocols((size_t)W);
-    std::vector<float> ovals((size_t)W);
-    std::vector<int> bucket_of[32];
     auto emit = [&](int n) {
         const int g = (n + 3) / 4;
-        const size_t at = P.vals.size();
+        const size_t at = O.vals.size();
         uint16_t absent = 0;
         for (int k = 0; k < n && cols[k] == absent; k++) absent++;
         for (int k = n; k < 4 * g; k++) { cols[k] = absent; vals[k] = 0.0f; }
@@ -282,40 +284,99 @@ int pack_panel(int64_t M, int64_t N, bool tiled, int W, Source &src, HostPanel &
                 }
             }
         }
-        P.vals.resize(at + (size_t)g * 4);
-        std::memcpy(&P.vals[at], ovals.data(), sizeof(float) * (size_t)g * 4);
-        if (P.index_bits == 8) {
-            P.idx8.resize(at + (size_t)g * 4);
-            for (int k = 0; k < 4 * g; k++) P.idx8[at + k] = (uint8_t)ocols[k];
+        O.vals.resize(at + (size_t)g * 4);
+        std::memcpy(&O.vals[at], ovals.data(), sizeof(float) * (size_t)g * 4);
+        if (index_bits == 8) {
+            O.idx8.resize(at + (size_t)g * 4);
+            for (int k = 0; k < 4 * g; k++) O.idx8[at + k] = (uint8_t)ocols[k];
         } else {
-            P.idx16.resize(at + (size_t)g * 4);
-            std::memcpy(&P.idx16[at], ocols.data(), sizeof(uint16_t) * (size_t)g * 4);
+            O.idx16.resize(at + (size_t)g * 4);
+            std::memcpy(&O.idx16[at], ocols.data(), sizeof(uint16_t) * (size_t)g * 4);
         }
-        P.groups += g;
+        O.groups += g;
         return g;
     };
 
-    for (int s = 0; s < P.slabs; s++) {
-        src.begin_slab(s);
-        for (int rb = 0; rb < P.row_blocks; rb++) {
-            const int64_t tile_first = P.groups;
-            if (tiled) P.off[(size_t)s * per_slab + rb] = (uint32_t)tile_first;
-            for (int r = 0; r < kTileRows; r++) {
-                const int64_t row = (int64_t)rb * kTileRows + r;
-                if (tiled) P.rel[((size_t)s * P.row_blocks + rb) * kTileRows + r] = (uint16_t)(P.groups - tile_first);
-                if (row >= M) continue;
-                if (!tiled) P.off[(size_t)s * per_slab + row] = (uint32_t)P.groups;
-                const int n = src.get(s, row, cols.data(), vals.data());
-                if (n) {
-                    const int g = emit(n);
-                    P.row_nnz[row] += n; P.row_groups[row] += g; P.row_segs[row] += 1; P.nnz += n; P.nonempty_segments++;
-                }
+    src.begin_slab(s);
+    for (int rb = 0; rb < row_blocks; rb++) {
+        const int64_t tile_first = O.groups;
+        if (tiled) O.off[(size_t)rb] = (uint32_t)tile_first;
+        for (int r = 0; r < kTileRows; r++) {
+            const int64_t row = (int64_t)rb * kTileRows + r;
+            if (tiled) O.rel[(size_t)rb * kTileRows + r] = (uint16_t)(O.groups - tile_first);
+            if (row >= M) continue;
+            if (!tiled) O.off[(size_t)row] = (uint32_t)O.groups;
+            const int n = src.get(s, row, cols.data(), vals.data());
+            if (n) {
+                const int g = emit(n);
+                st.nnz[row] += n; st.groups[row] += g; st.segs[row] += 1; O.nnz += n; O.segs++;
             }
-            if (P.groups - tile_first > 65535) return SPMV_ERR_UNSUPPORTED;   // u16 rel offsets
-            if (P.groups >= (int64_t)UINT32_MAX) return SPMV_ERR_UNSUPPORTED;
         }
-        P.off[(size_t)s * per_slab + (tiled ? P.row_blocks : M)] = (uint32_t)P.groups;
+        if (O.groups - tile_first > 65535) { O.rc = SPMV_ERR_UNSUPPORTED; return; }   // u16 rel offsets
+        if (O.groups >= (int64_t)UINT32_MAX) { O.rc = SPMV_ERR_UNSUPPORTED; return; }
     }
+    O.off[(size_t)(tiled ? row_blocks : M)] = (uint32_t)O.groups;
+}
+
+// Slabs are independent, so they are packed by a small pool of host threads (the reference packs
+// on one thread with vector<vector<float>> copies, awsp.cpp:30-46) and concatenated afterwards;
+// the result does not depend on the thread count.
+template <class Source>
+int pack_panel(int64_t M, int64_t N, bool tiled, int W, const Source &proto, HostPanel &P)
+{
+    if (W < kMinSlabCols || W > kMaxSlabCols || (W & (W - 1))) return SPMV_ERR_ARG;
+    P.M = M; P.N = N; P.tiled = tiled;
+    P.slab_cols = W;
+    P.index_bits = (W == 256) ? 8 : 16;
+    P.slabs = (int)((N + W - 1) / W);
+    P.row_blocks = (int)((M + kTileRows - 1) / kTileRows);
+    P.nnz = 0; P.groups = 0; P.nonempty_segments = 0;
+    P.vals.clear(); P.idx8.clear(); P.idx16.clear(); P.rel.clear();
+    const int64_t per_slab = tiled ? (P.row_blocks + 1) : (M + 1);
+
+    int n_threads = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    if (const char *e = std::getenv("SPMV_PACK_THREADS")) n_threads = std::max(1, std::atoi(e));
+    n_threads = std::max(1, std::min(n_threads, P.slabs));
+    std::vector<SlabOut> outs((size_t)P.slabs);
+    std::vector<RowStats> stats((size_t)n_threads);
+    for (RowStats &st : stats) { st.nnz.assign((size_t)M, 0); st.groups.assign((size_t)M, 0); st.segs.assign((size_t)M, 0); }
+    auto worker = [&](int t) {
+        Source src = proto;                                // per-thread scratch (CSR(A^T) row buckets)
+        for (int s = t; s < P.slabs; s += n_threads)
+            pack_slab(s, M, tiled, W, P.index_bits, P.row_blocks, src, outs[(size_t)s], stats[(size_t)t]);
+    };
+    if (n_threads == 1) worker(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_threads; t++) pool.emplace_back(worker, t);
+        for (std::thread &th : pool) th.join();
+    }
+
+    int64_t total = 0;
+    for (const SlabOut &o : outs) { if (o.rc) return o.rc; total += o.groups; }
+    if (total >= (int64_t)UINT32_MAX) return SPMV_ERR_UNSUPPORTED;
+    P.vals.resize((size_t)total * 4);
+    if (P.index_bits == 8) P.idx8.resize((size_t)total * 4); else P.idx16.resize((size_t)total * 4);
+    P.off.assign((size_t)P.slabs * per_slab, 0);
+    if (tiled) P.rel.assign((size_t)P.slabs * P.row_blocks * kTileRows, 0);
+    int64_t base = 0;
+    for (int s = 0; s < P.slabs; s++) {
+        const SlabOut &o = outs[(size_t)s];
+        if (o.groups) {
+            std::memcpy(&P.vals[(size_t)base * 4], o.vals.data(), sizeof(float) * (size_t)o.groups * 4);
+            if (P.index_bits == 8) std::memcpy(&P.idx8[(size_t)base * 4], o.idx8.data(), (size_t)o.groups * 4);
+            else std::memcpy(&P.idx16[(size_t)base * 4], o.idx16.data(), sizeof(uint16_t) * (size_t)o.groups * 4);
+        }
+        for (int64_t k = 0; k < per_slab; k++) P.off[(size_t)s * per_slab + k] = (uint32_t)(base + o.off[(size_t)k]);
+        if (tiled) std::memcpy(&P.rel[(size_t)s * P.row_blocks * kTileRows], o.rel.data(), sizeof(uint16_t) * o.rel.size());
+        base += o.groups;
+        P.nnz += o.nnz; P.nonempty_segments += o.segs;
+        outs[(size_t)s] = SlabOut();                       // release the slab's copy early
+    }
+    P.groups = total;
+    P.row_nnz.assign((size_t)M, 0); P.row_groups.assign((size_t)M, 0); P.row_segs.assign((size_t)M, 0);
+    for (const RowStats &st : stats)
+        for (int64_t r = 0; r < M; r++) { P.row_nnz[r] += st.nnz[r]; P.row_groups[r] += st.groups[r]; P.row_segs[r] += st.segs[r]; }
     return SPMV_OK;
 }
 } // namespace
