@@ -156,9 +156,10 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
             const uint4 m = list[r];
 #pragma unroll 1
             for (uint32_t g = m.x; g < m.y; g += 32) {
-                const int s = it++ & (kStages - 1);
+                const int s = it & (kStages - 1);
                 cp_async_wait<kStages - 1>();             // the oldest group (slot s) has landed
-                retire(s);
+                if (it >= kStages) retire(s);             // (the first kStages slots start empty)
+                it++;
                 const uint32_t gg = g + lane;
                 const bool ok = gg < m.y;
                 const uint32_t gs = ok ? gg : g;
@@ -200,9 +201,10 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
             const int total = __shfl_sync(kFull, pend, 31);
 #pragma unroll 1
             for (int k0 = 0; k0 < total; k0 += 32) {
-                const int s = it++ & (kStages - 1);
+                const int s = it & (kStages - 1);
                 cp_async_wait<kStages - 1>();
-                retire_mr(s);
+                if (it >= kStages) retire_mr(s);
+                it++;
                 // which row does flat position k0 + lane belong to?  rows ending inside the chunk
                 // set one bit each; rows that ended before it are counted by a ballot
                 const unsigned e = (unsigned)(pend - k0 - 1);
@@ -288,9 +290,13 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         SPMV_STAMP(wg, 2);
         cp_async_wait<0>();
         SPMV_STAMP(wg, 3);
+        {
+            const int pending = min(it, kStages);         // slots that hold a chunk: the last `pending` issued
 #pragma unroll 1
-        for (int k = 0; k < kStages; k++) {
-            if (MR) retire_mr(it++ & (kStages - 1)); else retire(it++ & (kStages - 1));
+            for (int k = it - pending; k < it; k++) {
+                if (MR) retire_mr(k & (kStages - 1)); else retire(k & (kStages - 1));
+            }
+            it = 0;                                       // the next piece starts with an empty ring
         }
         SPMV_STAMP(wg, 4);
 
