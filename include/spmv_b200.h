@@ -142,6 +142,16 @@ SPMV_API void spmv_plan_destroy(spmv_plan_t *plan);
 SPMV_API int spmv_plan_clone(const spmv_plan_t *plan, spmv_plan_t **out);
 
 /*
+ * Plan files (packing is O(M*N) host work the reference repeats on every call,
+ * e.g. awsp.cpp:3-49).  spmv_plan_save writes the packed format of a plan; spmv_plan_load uploads
+ * it again without re-packing and re-derives the launch geometry for the current device (opts as
+ * in spmv_plan_create_*).  A loaded plan computes bit-identical results.  Files are validated on
+ * load (sizes, offsets, index ranges); a damaged file fails with SPMV_ERR_ARG.
+ */
+SPMV_API int spmv_plan_save(const spmv_plan_t *plan, const char *path);
+SPMV_API int spmv_plan_load(const char *path, const spmv_options_t *opts, spmv_plan_t **out);
+
+/*
  * Bytes one call moves for a given activation vector (host copy of x):
  *   alg_bytes  — the format-independent figure of SURVEY §8d:
  *                8*nnz_t + 4*(N+1) + 4*M + 4*N   (wsp/tcsr: nnz_t = all stored nnz;

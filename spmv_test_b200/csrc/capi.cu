@@ -166,6 +166,35 @@ static bool opts_ok(const spmv_options_t *o)
 
 using namespace spmv;
 
+namespace {
+constexpr uint64_t kFileMagic = 0x3130504c50564d53ull;   // "SMVPLP01"
+
+struct FileWriter {
+    FILE *f; bool ok = true;
+    void bytes(const void *p, size_t n) { if (ok && n && fwrite(p, 1, n, f) != n) ok = false; }
+    template <class T> void pod(const T &v) { bytes(&v, sizeof v); }
+    template <class T> void vec(const std::vector<T> &v) { pod<uint64_t>(v.size()); bytes(v.data(), v.size() * sizeof(T)); }
+};
+struct FileReader {
+    FILE *f; bool ok = true; uint64_t limit;
+    void bytes(void *p, size_t n) { if (ok && n && fread(p, 1, n, f) != n) ok = false; }
+    template <class T> void pod(T &v) { bytes(&v, sizeof v); }
+    template <class T> void vec(std::vector<T> &v)
+    {
+        uint64_t n = 0; pod(n);
+        if (!ok || n * sizeof(T) > limit) { ok = false; return; }
+        v.resize((size_t)n); bytes(v.data(), (size_t)n * sizeof(T));
+    }
+};
+
+template <class T> int fetch(std::vector<T> &h, const void *dev, size_t count)
+{
+    h.resize(count);
+    if (count) SPMV_CUDA(cudaMemcpy(h.data(), dev, count * sizeof(T), cudaMemcpyDeviceToHost));
+    return SPMV_OK;
+}
+} // namespace
+
 extern "C" {
 
 int spmv_abi_version(void) { return SPMV_B200_ABI_VERSION; }
@@ -310,6 +339,152 @@ int spmv_plan_clone(const spmv_plan_t *src, spmv_plan_t **out)
         if (e != cudaSuccess) rc = cuda_error(e, "clone: stream/event");
     }
     if (rc) { spmv_plan_destroy(p); return rc; }
+    *out = p;
+    return SPMV_OK;
+}
+
+// ---- plan files -------------------------------------------------------------------------------
+// A plan file holds the packed format (the arrays resident in HBM plus the per-row statistics),
+// not the launch geometry: loading re-runs the geometry setup for the device at hand, so a file
+// written on one GPU model loads on another.  Little-endian, this library only.
+int spmv_plan_save(const spmv_plan_t *p, const char *path)
+{
+    if (!p || !path) return set_error(SPMV_ERR_ARG, "null argument");
+    int rc = SPMV_OK;
+    HostWsp w; HostPanel h; std::vector<float> dense;
+    if (p->variant == SPMV_WSP) {
+        w.M = p->M; w.N = p->N; w.nnz = p->nnz; w.groups = p->fmt_groups; w.index_bits = p->wsp.index_bits;
+        w.panels = p->wsp.panels; w.panel_rows = p->wsp.panel_rows;
+        rc = fetch(w.colptr, p->wsp.colptr, (size_t)w.panels * p->N + 1);
+        if (!rc) rc = fetch(w.vals, p->wsp.vals, (size_t)(w.groups + 1) * 4);
+        if (!rc) rc = w.index_bits == 16 ? fetch(w.idx16, p->wsp.idx, (size_t)(w.groups + 1) * 4)
+                                         : fetch(w.idx32, p->wsp.idx, (size_t)(w.groups + 1) * 4);
+    } else if (p->variant == SPMV_ASP) {
+        rc = fetch(dense, p->asp.A, (size_t)p->M * p->N);
+    } else {
+        const DevPanel &d = p->panel;
+        h.M = p->M; h.N = p->N; h.nnz = p->nnz; h.groups = p->fmt_groups; h.slab_cols = d.slab_cols;
+        h.index_bits = d.index_bits; h.slabs = d.slabs; h.row_blocks = d.row_blocks; h.tiled = d.tiled;
+        rc = fetch(h.off, d.off, (size_t)d.slabs * (d.tiled ? d.row_blocks + 1 : p->M + 1));
+        if (!rc && d.tiled) rc = fetch(h.rel, d.rel, (size_t)d.slabs * d.row_blocks * kTileRows);
+        if (!rc) rc = fetch(h.vals, d.vals, (size_t)h.groups * 4);
+        if (!rc) rc = d.index_bits == 8 ? fetch(h.idx8, d.idx, (size_t)h.groups * 4) : fetch(h.idx16, d.idx, (size_t)h.groups * 4);
+        h.row_nnz = p->row_nnz; h.row_groups = p->row_groups; h.row_segs = p->row_segs;
+    }
+    if (rc) return rc;
+    FILE *f = fopen(path, "wb");
+    if (!f) return set_error(SPMV_ERR_ARG, "cannot open %s for writing", path);
+    FileWriter fw{f};
+    fw.pod(kFileMagic); fw.pod<int32_t>(SPMV_B200_ABI_VERSION); fw.pod<int32_t>(p->variant);
+    fw.pod<int64_t>(p->M); fw.pod<int64_t>(p->N); fw.pod<int64_t>(p->nnz);
+    if (p->variant == SPMV_WSP) {
+        fw.pod<int64_t>(w.groups); fw.pod<int32_t>(w.index_bits); fw.pod<int32_t>(w.panels); fw.pod<int64_t>(w.panel_rows);
+        fw.vec(w.colptr); fw.vec(w.vals); fw.vec(w.idx16); fw.vec(w.idx32);
+    } else if (p->variant == SPMV_ASP) {
+        fw.vec(dense);
+    } else {
+        fw.pod<int64_t>(h.groups); fw.pod<int32_t>(h.slab_cols); fw.pod<int32_t>(h.index_bits); fw.pod<int32_t>(h.slabs);
+        fw.pod<int32_t>(h.row_blocks); fw.pod<int32_t>(h.tiled ? 1 : 0);
+        fw.vec(h.off); fw.vec(h.rel); fw.vec(h.vals); fw.vec(h.idx8); fw.vec(h.idx16);
+        fw.vec(h.row_nnz); fw.vec(h.row_groups); fw.vec(h.row_segs);
+    }
+    fw.pod(kFileMagic);
+    const bool ok = fw.ok;
+    if (fclose(f) != 0 || !ok) return set_error(SPMV_ERR_ARG, "write to %s failed", path);
+    return SPMV_OK;
+}
+
+int spmv_plan_load(const char *path, const spmv_options_t *opts, spmv_plan_t **out)
+{
+    if (!path || !out) return set_error(SPMV_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (!opts_ok(opts)) return set_error(SPMV_ERR_ARG, "bad spmv_options_t");
+    FILE *f = fopen(path, "rb");
+    if (!f) return set_error(SPMV_ERR_ARG, "cannot open %s", path);
+    fseek(f, 0, SEEK_END);
+    const long fsize = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    FileReader fr{f, true, (uint64_t)std::max<long>(fsize, 0)};
+    uint64_t magic = 0; int32_t abi = 0, variant = -1; int64_t M = 0, N = 0, nnz = 0;
+    fr.pod(magic); fr.pod(abi); fr.pod(variant); fr.pod(M); fr.pod(N); fr.pod(nnz);
+    auto fail = [&](const char *why) { fclose(f); return set_error(SPMV_ERR_ARG, "%s: %s", path, why); };
+    if (!fr.ok || magic != kFileMagic) return fail("not a plan file");
+    if (abi != SPMV_B200_ABI_VERSION) return fail("written by another ABI version");
+    spmv_plan *p = nullptr;
+    int rc = SPMV_OK;
+    try {
+        if (variant == SPMV_WSP) {
+            HostWsp w; w.M = M; w.N = N; w.nnz = nnz;
+            int32_t ib = 0, panels = 0;
+            fr.pod(w.groups); fr.pod(ib); fr.pod(panels); fr.pod(w.panel_rows);
+            w.index_bits = ib; w.panels = panels;
+            fr.vec(w.colptr); fr.vec(w.vals); fr.vec(w.idx16); fr.vec(w.idx32);
+            uint64_t tail = 0; fr.pod(tail);
+            const bool sane = fr.ok && tail == kFileMagic && panels >= 1 && (ib == 16 || ib == 32) && w.groups >= 0 &&
+                              w.colptr.size() == (size_t)panels * N + 1 && w.vals.size() == (size_t)(w.groups + 1) * 4 &&
+                              (ib == 16 ? w.idx16.size() : w.idx32.size()) == w.vals.size() && w.colptr.back() == (uint32_t)w.groups;
+            if (!sane) return fail("corrupt wsp plan file");
+            for (size_t i = 0; i + 1 < w.colptr.size(); i++) {
+                if (w.colptr[i] > w.colptr[i + 1]) return fail("corrupt wsp plan file (offsets)");
+                w.max_col_groups = std::max<int64_t>(w.max_col_groups, (int64_t)w.colptr[i + 1] - w.colptr[i]);
+            }
+            const uint32_t lim = (uint32_t)w.panel_rows;
+            if (ib == 16) { for (uint16_t v : w.idx16) if (v > lim) return fail("corrupt wsp plan file (row ids)"); }
+            else { for (uint32_t v : w.idx32) if (v > lim) return fail("corrupt wsp plan file (row ids)"); }
+            fclose(f); f = nullptr;
+            rc = plan_begin(variant, M, N, &p);
+            if (!rc) rc = setup_wsp(p, w, opts);
+        } else if (variant == SPMV_ASP) {
+            std::vector<float> dense;
+            fr.vec(dense);
+            uint64_t tail = 0; fr.pod(tail);
+            if (!fr.ok || tail != kFileMagic || dense.size() != (size_t)M * N) return fail("corrupt asp plan file");
+            fclose(f); f = nullptr;
+            rc = plan_begin(variant, M, N, &p);
+            if (!rc) {
+                p->nnz = M * N; p->asp.ld = N;
+                rc = dev_alloc(p, &p->asp.A, (size_t)M * N, false);
+                if (!rc && M * N > 0) {
+                    cudaError_t e = cudaMemcpy(p->asp.A, dense.data(), dense.size() * 4, cudaMemcpyHostToDevice);
+                    if (e != cudaSuccess) rc = cuda_error(e, "cudaMemcpy(A)");
+                }
+                p->device_bytes += M * N * 4;
+                if (!rc) rc = configure_asp(p, opts);
+            }
+        } else if (variant == SPMV_AWSP || variant == SPMV_TCSR) {
+            HostPanel h; h.M = M; h.N = N; h.nnz = nnz;
+            int32_t sc = 0, ib = 0, slabs = 0, rb = 0, tiled = 0;
+            fr.pod(h.groups); fr.pod(sc); fr.pod(ib); fr.pod(slabs); fr.pod(rb); fr.pod(tiled);
+            h.slab_cols = sc; h.index_bits = ib; h.slabs = slabs; h.row_blocks = rb; h.tiled = tiled != 0;
+            fr.vec(h.off); fr.vec(h.rel); fr.vec(h.vals); fr.vec(h.idx8); fr.vec(h.idx16);
+            fr.vec(h.row_nnz); fr.vec(h.row_groups); fr.vec(h.row_segs);
+            uint64_t tail = 0; fr.pod(tail);
+            const size_t per_slab = h.tiled ? (size_t)rb + 1 : (size_t)M + 1;
+            const bool sane = fr.ok && tail == kFileMagic && (ib == 8 || ib == 16) && sc >= kMinSlabCols && sc <= kMaxSlabCols &&
+                              !(sc & (sc - 1)) && (ib == 8) == (sc == 256) && slabs == (int32_t)((N + sc - 1) / sc) &&
+                              rb == (int32_t)((M + kTileRows - 1) / kTileRows) && h.groups >= 0 &&
+                              h.off.size() == (size_t)slabs * per_slab && h.vals.size() == (size_t)h.groups * 4 &&
+                              (ib == 8 ? h.idx8.size() : h.idx16.size()) == h.vals.size() &&
+                              h.rel.size() == (h.tiled ? (size_t)slabs * rb * kTileRows : 0) &&
+                              h.row_nnz.size() == (size_t)M && h.row_groups.size() == (size_t)M && h.row_segs.size() == (size_t)M &&
+                              (variant == SPMV_TCSR) == h.tiled;
+            if (!sane) return fail("corrupt panel plan file");
+            for (size_t i = 0; i + 1 < h.off.size(); i++)
+                if (h.off[i] > h.off[i + 1] || h.off[i + 1] > (uint32_t)h.groups) return fail("corrupt panel plan file (offsets)");
+            if (ib == 16) for (uint16_t v : h.idx16) if (v >= sc) return fail("corrupt panel plan file (column ids)");
+            for (int32_t v : h.row_segs) h.nonempty_segments += v;
+            fclose(f); f = nullptr;
+            rc = plan_begin(variant, M, N, &p);
+            if (!rc) rc = setup_panel(p, h, opts);
+        } else {
+            return fail("unknown variant");
+        }
+        if (!rc) rc = plan_finish(p);
+    } catch (const std::bad_alloc &) {
+        rc = set_error(SPMV_ERR_NOMEM, "out of host memory while loading");
+    }
+    if (f) fclose(f);
+    if (rc) { if (p) spmv_plan_destroy(p); return rc; }
     *out = p;
     return SPMV_OK;
 }

@@ -38,6 +38,7 @@ struct DevWsp {
     int warps_per_col = 1;
     bool x_in_smem = true;
     int panels = 1;             // row panels (tall matrices)
+    int64_t panel_rows = 0;
 };
 
 struct DevAsp {

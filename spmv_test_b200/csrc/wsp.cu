@@ -395,6 +395,7 @@ int configure_wsp(spmv_plan *p, const HostWsp &w, const spmv_options_t *o)
     p->wsp.index_bits = w.index_bits;
     s->panels = w.panels;
     p->wsp.panels = w.panels;
+    p->wsp.panel_rows = w.panels > 1 ? w.panel_rows : w.M;
     s->panel_rows = w.panels > 1 ? w.panel_rows : w.M;
     if (w.panels > 1) {
         SPMV_CUDA(cudaMalloc(&s->partial, (size_t)w.panels * std::max<int64_t>(w.N, 1) * sizeof(float)));

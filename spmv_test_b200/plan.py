@@ -68,6 +68,16 @@ class Plan:
                                          _opts(**opts), C.byref(h)))
         return cls(h.value)
 
+    def save(self, path):
+        """Writes the packed format to `path` (no re-packing on load)."""
+        check(lib().spmv_plan_save(self._h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path, **opts):
+        h = C.c_void_p()
+        check(lib().spmv_plan_load(str(path).encode(), _opts(**opts), C.byref(h)))
+        return cls(h.value)
+
     def clone(self):
         h = C.c_void_p()
         check(lib().spmv_plan_clone(self._h, C.byref(h)))

@@ -350,3 +350,39 @@ def test_wsp_row_panels_tall(S):
             assert p.run_host(x).tobytes() == y.tobytes()
             err = np.abs(y.astype(np.float64) - y_ref)
             assert float(np.max(err / (s + 1e-30))) <= 1e-5, (M, N)
+
+
+def test_plan_save_load_roundtrip(S, tmp_path):
+    """A plan file holds the packed format; a loaded plan computes bit-identical results and a
+    damaged file is rejected."""
+    A = ob.gen_matrix(768, 1024, 0.8, 81)
+    x = ob.gen_vector(768, 0.5, 82)
+    for v in VARIANTS:
+        path = tmp_path / f"{v}.plan"
+        with S.Plan.from_dense(v, A) as p:
+            y = p.run_host(x)
+            p.save(path)
+            info = p.info()
+        with S.Plan.load(path) as q:
+            assert q.run_host(x).tobytes() == y.tobytes(), v
+            qi = q.info()
+            assert (qi["M"], qi["N"], qi["nnz"], qi["device_bytes"]) == (info["M"], info["N"], info["nnz"], info["device_bytes"])
+            assert q.traffic(x) == S.Plan.load(path).traffic(x)
+        raw = bytearray(path.read_bytes())
+        raw[len(raw) // 2] ^= 0xFF
+        bad = tmp_path / "bad.plan"
+        bad.write_bytes(bytes(raw[: len(raw) - 9]))
+        with pytest.raises(S.SpmvError):
+            S.Plan.load(bad)
+    with pytest.raises(S.SpmvError):
+        S.Plan.load(tmp_path / "missing.plan")
+    # tall wsp (row panels) and a very sparse awsp (multi-row chunks) survive the round trip too
+    from spmv_test_b200 import synth
+    cp, ri, va = synth.bernoulli_csc(40000, 256, 0.01, 83)
+    x2 = ob.gen_vector(40000, 0.5, 84)
+    for v in ("wsp", "awsp"):
+        with S.Plan.from_csc(v, 40000, 256, cp, ri, va) as p:
+            y = p.run_host(x2)
+            p.save(tmp_path / "t.plan")
+        with S.Plan.load(tmp_path / "t.plan") as q:
+            assert q.run_host(x2).tobytes() == y.tobytes(), v
