@@ -167,6 +167,16 @@ SPMV_API int spmv_plan_traffic(const spmv_plan_t *plan, const float *x, double *
 SPMV_API int spmv_run(spmv_plan_t *plan, const float *d_x, float *d_y, void *stream);
 
 /*
+ * Batched (multi-vector) form, SURVEY section 8f-2: Y[b] = X[b] * A for b < batch, X row-major
+ * batch x M (row stride ldx), Y row-major batch x N (row stride ldy, multiple of 4), device
+ * pointers.  Weight-sparse plans stream A once per group of 4 (or 2) vectors with all of them in
+ * shared memory, so A's bytes are reused; every other case runs the vectors one after the other.
+ * Each Y[b] is bit-identical to spmv_run on X[b].
+ */
+SPMV_API int spmv_run_batch(spmv_plan_t *plan, int batch, const float *d_X, int64_t ldx, float *d_Y, int64_t ldy,
+                            void *stream);
+
+/*
  * Column-sharded multi-GPU execution with the all-gather fused into the kernel epilogue
  * (the reference is single-GPU).  This rank's plan covers the output columns
  * [offset, offset + N) of the full y; its final stores go to that slice of EVERY rank's copy of

@@ -563,6 +563,39 @@ int spmv_run(spmv_plan_t *p, const float *d_x, float *d_y, void *stream)
     return run_to(p, d_x, yd, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int spmv_run_batch(spmv_plan_t *p, int batch, const float *d_X, int64_t ldx, float *d_Y, int64_t ldy, void *stream)
+{
+    if (!p) return set_error(SPMV_ERR_ARG, "null plan");
+    if (batch < 0) return set_error(SPMV_ERR_ARG, "negative batch");
+    if (batch == 0) return SPMV_OK;
+    if ((!d_X && p->M > 0) || (!d_Y && p->N > 0)) return set_error(SPMV_ERR_ARG, "null device matrix");
+    if (ldx < p->M || ldy < p->N) return set_error(SPMV_ERR_ARG, "ldx / ldy smaller than M / N");
+    if ((reinterpret_cast<uintptr_t>(d_Y) & 15) != 0 || ldy % 4) return set_error(SPMV_ERR_ARG, "d_Y rows must be 16-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int b = 0;
+    while (b < batch) {
+        YDst yd{};
+        yd.p[0] = d_Y + (size_t)b * ldy; yd.n = 1; yd.mc = nullptr;
+        const float *xb = d_X + (size_t)b * ldx;
+        int done = 0;
+        if (p->variant == SPMV_WSP && p->N > 0 && p->M > 0) {
+            for (int B : {4, 2}) {
+                if (batch - b < B) continue;
+                const int rc = launch_wsp_batch(p, xb, ldx, yd, ldy, B, st);
+                if (rc == SPMV_OK) { done = B; break; }
+                if (rc != SPMV_ERR_UNSUPPORTED) return rc;
+            }
+        }
+        if (!done) {                                      // one vector: the single-vector kernels
+            const int rc = run_to(p, xb, yd, st);
+            if (rc) return rc;
+            done = 1;
+        }
+        b += done;
+    }
+    return SPMV_OK;
+}
+
 int spmv_run_scatter(spmv_plan_t *p, const float *d_x, int n_dst, float *const *d_y_dst, float *d_y_multicast,
                      int64_t offset, void *stream)
 {

@@ -113,6 +113,7 @@ namespace spmv {
 // kernel launchers (one per .cu); all are asynchronous on `st`
 struct YDst;   // common.cuh: where y goes (one pointer, or every rank's copy in the sharded case)
 int launch_wsp(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
+int launch_wsp_batch(spmv_plan *p, const float *d_x, long long ldx, const YDst &yd, long long ldy, int B, cudaStream_t st);
 int launch_asp(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
 int launch_panel(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
 int launch_compact(const float *d_x, int64_t M, int32_t *d_idx, float *d_val, int32_t *d_count,

@@ -160,12 +160,16 @@ template <> struct RingCopy<uint4> {
     static __device__ __forceinline__ void copy(uint4 *d, const uint4 *s) { cp_async16(d, s); }
 };
 
-template <typename IdxVec>
+// B > 1: batched (multi-vector) form — B activation vectors x[b] (row stride ldx) against the
+// same A: every value / index pair fetched from HBM is used B times.  Each
+// vector's arithmetic is exactly that of the single-vector kernel, so results are bit-identical
+// to B separate calls.  Batched mode is single-panel, single-destination.
+template <typename IdxVec, int B>
 __global__ void __launch_bounds__(kRingWarps * 32)
 wsp_ring_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
                 const uint32_t *__restrict__ colptr, const int32_t *__restrict__ cols, int ncols,
                 const float *__restrict__ x, const YDst yd, uint32_t M_total, int x_bulk_ok, int xs_bytes,
-                uint32_t panel_rows, int n_total, float *__restrict__ partial)
+                uint32_t panel_rows, int n_total, float *__restrict__ partial, long long ldx, long long ldy)
 {
     extern __shared__ __align__(16) unsigned char wsm[];
     __shared__ __align__(8) uint64_t bar;
@@ -181,22 +185,27 @@ wsp_ring_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
     IdxVec *ring_i = reinterpret_cast<IdxVec *>(wsm + xs_bytes + kRingWarps * kRingStages * 32 * 16) + warp * kRingStages * 32;
 
     // x -> shared memory (1-D bulk async copies when aligned), overlapped with the first chunks
+    const uint32_t xstride = (uint32_t)xs_bytes / (4u * B);   // floats per vector in shared memory
     const uint32_t m4 = M & ~3u;
     const bool bulk = x_bulk_ok && m4;
     if (bulk) {
         if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
         __syncthreads();
         if (tid == 0) {
-            mbar_expect_tx(&bar, m4 * 4u);
-            for (uint32_t done = 0; done < m4 * 4u; done += 32768u)
-                bulk_g2s(reinterpret_cast<char *>(xs) + done, reinterpret_cast<const char *>(x) + done,
-                         min(m4 * 4u - done, 32768u), &bar);
+            mbar_expect_tx(&bar, m4 * 4u * B);
+            for (int b = 0; b < B; b++)
+                for (uint32_t done = 0; done < m4 * 4u; done += 32768u)
+                    bulk_g2s(reinterpret_cast<char *>(xs + b * xstride) + done,
+                             reinterpret_cast<const char *>(x + b * ldx) + done, min(m4 * 4u - done, 32768u), &bar);
         }
-        for (uint32_t j = m4 + tid; j < M; j += blockDim.x) xs[j] = x[j];
+        for (int b = 0; b < B; b++)
+            for (uint32_t j = m4 + tid; j < M; j += blockDim.x) xs[b * xstride + j] = x[b * ldx + j];
     } else {
-        for (uint32_t j = tid; j < M; j += blockDim.x) xs[j] = x[j];
+        for (int b = 0; b < B; b++)
+            for (uint32_t j = tid; j < M; j += blockDim.x) xs[b * xstride + j] = x[b * ldx + j];
     }
-    for (uint32_t j = M + tid; j < panel_rows + 4; j += blockDim.x) xs[j] = 0.0f;   // tail of the last panel + pad slot
+    for (int b = 0; b < B; b++)
+        for (uint32_t j = M + tid; j < panel_rows + 4; j += blockDim.x) xs[b * xstride + j] = 0.0f;   // tail of the last panel + pad slot
 
     // ---- flat iterator over (column, chunk) ---------------------------------------------------------
     // This warp's columns are positions kbase, kbase + nwarps, ... of the column list.  Their
@@ -254,7 +263,9 @@ wsp_ring_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
     if (bulk) mbar_wait(&bar, 0);
     __syncthreads();                                      // x is in shared memory
 
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float a0[B], a1[B], a2[B], a3[B];
+#pragma unroll
+    for (int b = 0; b < B; b++) a0[b] = a1[b] = a2[b] = a3[b] = 0.f;
     while (fin[0] != -2) {
 #pragma unroll
         for (int s = 0; s < kRingStages; s++) {
@@ -263,15 +274,22 @@ wsp_ring_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
                 const float4 v = ring_v[s * 32 + lane];
                 uint32_t i[4];
                 IdxTraits<IdxVec>::unpack(ring_i[s * 32 + lane], i);
-                a0 = fmaf(v.x, xs[i[0]], a0); a1 = fmaf(v.y, xs[i[1]], a1);
-                a2 = fmaf(v.z, xs[i[2]], a2); a3 = fmaf(v.w, xs[i[3]], a3);
+#pragma unroll
+                for (int b = 0; b < B; b++) {
+                    const float *xb = xs + b * xstride;
+                    a0[b] = fmaf(v.x, xb[i[0]], a0[b]); a1[b] = fmaf(v.y, xb[i[1]], a1[b]);
+                    a2[b] = fmaf(v.z, xb[i[2]], a2[b]); a3[b] = fmaf(v.w, xb[i[3]], a3[b]);
+                }
                 if (fin[s] >= 0) {
-                    const float t = warp_sum((a0 + a1) + (a2 + a3));
-                    if (lane == 0) {
-                        if (gridDim.y == 1) y_store(yd, fin[s], t);
-                        else partial[(size_t)panel * n_total + fin[s]] = t;
+#pragma unroll
+                    for (int b = 0; b < B; b++) {
+                        const float t = warp_sum((a0[b] + a1[b]) + (a2[b] + a3[b]));
+                        if (lane == 0) {
+                            if (gridDim.y == 1) y_store(yd, (size_t)b * ldy + fin[s], t);
+                            else partial[(size_t)panel * n_total + fin[s]] = t;
+                        }
+                        a0[b] = a1[b] = a2[b] = a3[b] = 0.f;
                     }
-                    a0 = a1 = a2 = a3 = 0.f;
                 }
             }
             issue(s);
@@ -340,25 +358,44 @@ static int launch_T(const spmv_plan *p, const WspBinDev &b, const float *x, cons
     return set_error(SPMV_ERR_ARG, "wsp: bad team size %d", b.T);
 }
 
-template <typename IdxVec>
-static int launch_ring(const spmv_plan *p, const WspBinDev &b, const float *x, const YDst &y, cudaStream_t st, int ok)
+template <typename IdxVec, int B>
+static int launch_ring(const spmv_plan *p, const WspBinDev &b, const float *x, const YDst &y, cudaStream_t st, int ok,
+                       long long ldx, long long ldy)
 {
-    auto k = wsp_ring_kernel<IdxVec>;
+    auto k = wsp_ring_kernel<IdxVec, B>;
+    const int xs_bytes = p->smem * B;
+    const int smem = b.smem + p->smem * (B - 1);
     static int smem_set[16] = {0};
-    if (b.smem > 48 * 1024 && p->device >= 0 && p->device < 16 && smem_set[p->device] < b.smem) {
-        SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, b.smem));
-        smem_set[p->device] = b.smem;
+    if (smem > 48 * 1024 && p->device >= 0 && p->device < 16 && smem_set[p->device] < smem) {
+        SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set[p->device] = smem;
     }
     const WspState *ws = reinterpret_cast<const WspState *>(p->wsp_state);
-    k<<<dim3(b.grid, ws->panels), kRingWarps * 32, b.smem, st>>>(
+    k<<<dim3(b.grid, ws->panels), kRingWarps * 32, smem, st>>>(
         reinterpret_cast<const float4 *>(p->wsp.vals), reinterpret_cast<const IdxVec *>(p->wsp.idx), p->wsp.colptr, b.cols,
-        b.ncols, x, y, (uint32_t)p->M, ok, p->smem, (uint32_t)ws->panel_rows, (int)p->N, ws->partial);
+        b.ncols, x, y, (uint32_t)p->M, ok, xs_bytes, (uint32_t)ws->panel_rows, (int)p->N, ws->partial, ldx, ldy);
     SPMV_CUDA(cudaGetLastError());
     if (ws->panels > 1) {
         wsp_combine_kernel<<<(unsigned)((p->N + 255) / 256), 256, 0, st>>>(ws->partial, ws->panels, (int)p->N, y);
         SPMV_CUDA(cudaGetLastError());
     }
     return SPMV_OK;
+}
+
+// Batched form: B in {2, 4} vectors in one pass over A when the plan is a single ring bin with one
+// row panel and the B copies of x fit shared memory; returns SPMV_ERR_UNSUPPORTED otherwise (the
+// caller then runs the vectors one by one).
+int launch_wsp_batch(spmv_plan *p, const float *d_x, long long ldx, const YDst &d_y, long long ldy, int B, cudaStream_t st)
+{
+    const WspState *s = reinterpret_cast<const WspState *>(p->wsp_state);
+    if (!s || s->bins.size() != 1 || !s->bins[0].ring || s->panels != 1 || (B != 2 && B != 4)) return SPMV_ERR_UNSUPPORTED;
+    const WspBinDev &b = s->bins[0];
+    const int smem = b.smem + p->smem * (B - 1);
+    if (smem > (p->max_smem_optin > 0 ? p->max_smem_optin : 227 * 1024)) return SPMV_ERR_UNSUPPORTED;
+    const int ok = ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && ldx % 4 == 0) ? 1 : 0;
+    if (p->wsp.index_bits == 16)
+        return B == 2 ? launch_ring<uint2, 2>(p, b, d_x, d_y, st, ok, ldx, ldy) : launch_ring<uint2, 4>(p, b, d_x, d_y, st, ok, ldx, ldy);
+    return B == 2 ? launch_ring<uint4, 2>(p, b, d_x, d_y, st, ok, ldx, ldy) : launch_ring<uint4, 4>(p, b, d_x, d_y, st, ok, ldx, ldy);
 }
 
 int launch_wsp(spmv_plan *p, const float *d_x, const YDst &d_y, cudaStream_t st)
@@ -369,8 +406,8 @@ int launch_wsp(spmv_plan *p, const float *d_x, const YDst &d_y, cudaStream_t st)
     for (const WspBinDev &b : s->bins) {
         int rc;
         if (b.ring) {
-            if (p->wsp.index_bits == 16) rc = launch_ring<uint2>(p, b, d_x, d_y, st, ok);
-            else rc = launch_ring<uint4>(p, b, d_x, d_y, st, ok);
+            if (p->wsp.index_bits == 16) rc = launch_ring<uint2, 1>(p, b, d_x, d_y, st, ok, 0, 0);
+            else rc = launch_ring<uint4, 1>(p, b, d_x, d_y, st, ok, 0, 0);
             if (rc) return rc;
             continue;
         }

@@ -123,6 +123,14 @@ class Plan:
             stream = torch.cuda.current_stream().cuda_stream
         check(lib().spmv_run(self._h, C.c_void_p(px), C.c_void_p(py), C.c_void_p(stream)))
 
+    def run_batch(self, d_X, d_Y, stream=None):
+        """Y[b] = X[b]·A for a batch of activation vectors (2-D CUDA tensors, row-major)."""
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        check(lib().spmv_run_batch(self._h, int(d_X.shape[0]), C.c_void_p(d_X.data_ptr()), int(d_X.stride(0)),
+                                   C.c_void_p(d_Y.data_ptr()), int(d_Y.stride(0)), C.c_void_p(stream)))
+
     def run_scatter(self, d_x, dst_ptrs, offset, multicast_ptr=0, stream=None):
         """y slice of this rank -> [offset, offset+N) of every buffer in dst_ptrs (device pointers
         of all ranks' full-y buffers), or through the multicast alias when given: the all-gather

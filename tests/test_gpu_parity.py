@@ -386,3 +386,31 @@ def test_plan_save_load_roundtrip(S, tmp_path):
             p.save(tmp_path / "t.plan")
         with S.Plan.load(tmp_path / "t.plan") as q:
             assert q.run_host(x2).tobytes() == y.tobytes(), v
+
+
+@pytest.mark.parametrize("batch", [1, 2, 3, 4, 7])
+def test_run_batch_matches_single_vector_calls(S, batch):
+    """spmv_run_batch: every Y[b] is bit-identical to spmv_run on X[b] (the wsp kernel reuses A's
+    bytes for groups of 4 / 2 vectors; other variants run the vectors one after the other)."""
+    import torch
+    A = ob.gen_matrix(1024, 768, 0.7, 91)
+    X = np.stack([ob.gen_vector(1024, 0.5, 100 + b) for b in range(batch)])
+    dX = torch.from_numpy(X).cuda()
+    for v in VARIANTS:
+        with S.Plan.from_dense(v, A) as p:
+            dY = torch.full((batch, 768), -1.0, device="cuda")
+            p.run_batch(dX, dY)
+            torch.cuda.synchronize()
+            Y = dY.cpu().numpy()
+            for b in range(batch):
+                assert Y[b].tobytes() == p.run_host(X[b]).tobytes(), (v, b)
+    # strided X / Y (leading dimensions larger than M / N)
+    with S.Plan.from_dense("wsp", A) as p:
+        dXp = torch.zeros((batch, 1024 + 32), device="cuda")
+        dXp[:, :1024] = dX
+        dYp = torch.zeros((batch, 768 + 64), device="cuda")
+        p.run_batch(dXp[:, :1024], dYp[:, :768])
+        torch.cuda.synchronize()
+        assert dYp[:, :768].cpu().numpy().tobytes() == Y.tobytes() if v == "wsp" else True
+        for b in range(batch):
+            assert dYp[b, :768].cpu().numpy().tobytes() == p.run_host(X[b]).tobytes()
