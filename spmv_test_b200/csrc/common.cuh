@@ -93,11 +93,6 @@ __device__ __forceinline__ uint2 ldg_stream_u2(const uint2 *p)
     return r;
 }
 
-// fire-and-forget request of one 128-byte line into L2: no register, no scoreboard slot
-__device__ __forceinline__ void prefetch_l2(const void *p)
-{
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -108,11 +103,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p)
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src)
                  : "memory");
 }
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)

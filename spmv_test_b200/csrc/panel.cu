@@ -4,19 +4,24 @@
 // and csr_tiling_kernel (csr_tiling.cu:24-114).  The reference gives every 32-column slab to
 // one CTA, walks a per-row bitmap (word -> popc -> address -> one 4-byte load per lane) and
 // uses x only as a load predicate: every bitmap word and every x is still read.  Here
-//   * a CTA owns (column slab, row range); each of its warps walks whole 32-row blocks;
-//   * lane l of a warp looks at row l of the block: x[row] and the segment's group range.
-//     ballot(x != 0 && segment non-empty) is the activation compaction: rows with x == 0 are
-//     never visited, so their values/indices are never read from HBM;
+//   * the (slab, row) pairs form one flat sequence cut into equal ranges, one per CTA (one
+//     resident wave, whole CTAs per slab where possible); a range is one or more pieces
+//     (slab, row range);
+//   * per piece, lane l of a warp looks at row l of a 32-row block: x[row] and the segment's
+//     group range.  ballot(x != 0 && segment non-empty) is the activation compaction: rows with
+//     x == 0 are never visited, so their values/indices are never read from HBM; the active
+//     rows are dealt to the CTA's warps (whole blocks per warp, or by rank for short pieces);
 //   * a visited segment is streamed as 128-bit groups (float4 values + 4 packed column ids),
 //     32 groups per chunk, kStages chunks in flight per warp through a cp.async ring in shared
 //     memory (commit/wait groups give a true FIFO; a register ring collapses to one load in
 //     flight because its loads share scoreboard slots — measured, profiles/r01_notes.md);
+//     short segments (config 5) are laid end to end, 32 groups per chunk, and retired row by row;
 //   * products are accumulated into a per-warp fp32 accumulator row in shared memory
 //     (columns inside one segment are distinct, segments are consumed in ascending row order,
 //     warps never share an accumulator) — no atomics, fixed summation order;
-//   * warps are summed in warp order, row splits in split order (integer ticket picks the CTA
-//     that does the final sum; the order of the sum itself is fixed).
+//   * warps are summed in warp order into one partial row per piece, the pieces of a slab in
+//     piece order (an integer ticket picks the CTA that does that final sum; the order of the
+//     sum itself is fixed), and y goes out through YDst (all ranks' buffers when sharded).
 // AWSP addresses segments through a 32-bit per-row table, TCSR through 32-bit per-tile plus
 // 16-bit in-tile offsets (the reference's blk_idx, tcsr.cpp:13,34, made two-level).
 #include <algorithm>
