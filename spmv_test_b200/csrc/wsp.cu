@@ -44,12 +44,13 @@ template <> struct IdxTraits<uint4> {   // 4 x u32
     static __device__ __forceinline__ uint4 pad(uint32_t M) { return make_uint4(M, M, M, M); }
 };
 
-// T threads cooperate on one output column.  XS: x lives in shared memory.
+// T threads cooperate on one output column.  XS: x lives in shared memory.  (bid, nblocks):
+// this CTA's position among the CTAs working on the same column list.
 template <typename IdxVec, int T, bool XS>
-__global__ void __launch_bounds__(kWspBlock)
-wsp_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
-           const uint32_t *__restrict__ colptr, const int32_t *__restrict__ cols, int ncols,
-           const float *__restrict__ x, const YDst yd, uint32_t M, int x_bulk_ok)
+__device__ __forceinline__ void
+wsp_body(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
+         const uint32_t *__restrict__ colptr, const int32_t *__restrict__ cols, int ncols,
+         const float *__restrict__ x, const YDst &yd, uint32_t M, int x_bulk_ok, int bid, int nblocks)
 {
     extern __shared__ __align__(16) float xs[];          // M + 1 (+pad) floats when XS
     __shared__ __align__(8) uint64_t bar;
@@ -81,8 +82,8 @@ wsp_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
     const int team_local = tid / T;
     const int tl = tid % T;
     const int lane = tid & 31;
-    const int team = blockIdx.x * kTeams + team_local;
-    const int nteams = gridDim.x * kTeams;
+    const int team = bid * kTeams + team_local;
+    const int nteams = nblocks * kTeams;
 
     // Issue the first column's loads before waiting for x: the A stream does not depend on it.
     if (XS) {
@@ -140,6 +141,49 @@ wsp_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
             for (int s = T / 2; s >= 1; s >>= 1) acc += __shfl_xor_sync(kFull, acc, s);
             if (tl == 0) y_store(yd, c, acc);
         }
+    }
+}
+
+template <typename IdxVec, int T, bool XS>
+__global__ void __launch_bounds__(kWspBlock)
+wsp_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
+           const uint32_t *__restrict__ colptr, const int32_t *__restrict__ cols, int ncols,
+           const float *__restrict__ x, const YDst yd, uint32_t M, int x_bulk_ok)
+{
+    wsp_body<IdxVec, T, XS>(vals, idx, colptr, cols, ncols, x, yd, M, x_bulk_ok, blockIdx.x, gridDim.x);
+}
+
+// All length bins of a skewed matrix in ONE launch (x gathered through L2): a CTA finds its bin
+// from its block index and runs that bin's team size.  Seven launches with seven ramps and tails
+// become one (BASELINE config 4).
+constexpr int kMaxBins = 8;
+struct BinTable {
+    int n;
+    int first_cta[kMaxBins + 1];
+    int T[kMaxBins];
+    int ncols[kMaxBins];
+    const int32_t *cols[kMaxBins];
+};
+
+template <typename IdxVec>
+__global__ void __launch_bounds__(kWspBlock)
+wsp_merged_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
+                  const uint32_t *__restrict__ colptr, const BinTable tb, const float *__restrict__ x,
+                  const YDst yd, uint32_t M)
+{
+    int b = 0;
+    while (b + 1 < tb.n && (int)blockIdx.x >= tb.first_cta[b + 1]) b++;
+    const int bid = blockIdx.x - tb.first_cta[b], nb = tb.first_cta[b + 1] - tb.first_cta[b];
+    const int32_t *cols = tb.cols[b];
+    const int ncols = tb.ncols[b];
+    switch (tb.T[b]) {
+    case 4: wsp_body<IdxVec, 4, false>(vals, idx, colptr, cols, ncols, x, yd, M, 0, bid, nb); break;
+    case 8: wsp_body<IdxVec, 8, false>(vals, idx, colptr, cols, ncols, x, yd, M, 0, bid, nb); break;
+    case 16: wsp_body<IdxVec, 16, false>(vals, idx, colptr, cols, ncols, x, yd, M, 0, bid, nb); break;
+    case 32: wsp_body<IdxVec, 32, false>(vals, idx, colptr, cols, ncols, x, yd, M, 0, bid, nb); break;
+    case 64: wsp_body<IdxVec, 64, false>(vals, idx, colptr, cols, ncols, x, yd, M, 0, bid, nb); break;
+    case 128: wsp_body<IdxVec, 128, false>(vals, idx, colptr, cols, ncols, x, yd, M, 0, bid, nb); break;
+    default: wsp_body<IdxVec, 256, false>(vals, idx, colptr, cols, ncols, x, yd, M, 0, bid, nb); break;
     }
 }
 
@@ -403,6 +447,25 @@ int launch_wsp(spmv_plan *p, const float *d_x, const YDst &d_y, cudaStream_t st)
     if (p->N == 0) return SPMV_OK;
     const WspState *s = reinterpret_cast<const WspState *>(p->wsp_state);
     const int ok = ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) ? 1 : 0;
+    if (!p->wsp.x_in_smem && s->bins.size() > 1 && (int)s->bins.size() <= kMaxBins) {
+        BinTable tb{};
+        tb.n = (int)s->bins.size();
+        int total = 0;
+        for (int i = 0; i < tb.n; i++) {
+            const WspBinDev &b = s->bins[(size_t)i];
+            tb.first_cta[i] = total; tb.T[i] = b.T; tb.ncols[i] = b.ncols; tb.cols[i] = b.cols;
+            total += b.grid;
+        }
+        tb.first_cta[tb.n] = total;
+        if (p->wsp.index_bits == 16)
+            wsp_merged_kernel<uint2><<<total, kWspBlock, 0, st>>>(reinterpret_cast<const float4 *>(p->wsp.vals),
+                reinterpret_cast<const uint2 *>(p->wsp.idx), p->wsp.colptr, tb, d_x, d_y, (uint32_t)p->M);
+        else
+            wsp_merged_kernel<uint4><<<total, kWspBlock, 0, st>>>(reinterpret_cast<const float4 *>(p->wsp.vals),
+                reinterpret_cast<const uint4 *>(p->wsp.idx), p->wsp.colptr, tb, d_x, d_y, (uint32_t)p->M);
+        SPMV_CUDA(cudaGetLastError());
+        return SPMV_OK;
+    }
     for (const WspBinDev &b : s->bins) {
         int rc;
         if (b.ring) {
@@ -502,6 +565,7 @@ int configure_wsp(spmv_plan *p, const HostWsp &w, const spmv_options_t *o)
         s->bins.push_back(d);
     }
     p->kernels_per_run = (int)s->bins.size() + (w.panels > 1 ? 1 : 0);
+    if (!p->wsp.x_in_smem && s->bins.size() > 1 && (int)s->bins.size() <= kMaxBins) p->kernels_per_run = 1;   // merged launch
     p->grid = dim3(s->bins.empty() ? 1 : s->bins[0].grid, 1, 1);
     p->wsp.warps_per_col = s->bins.empty() ? 0 : std::max(1, s->bins[0].T / 32);
     p->wsp_team = s->bins.empty() ? 0 : s->bins[0].T;
