@@ -189,7 +189,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         const float p = __uint_as_float(mine.x);
         const bool live = lane < info.x;
         for (uint32_t pass = 0; pass < info.y; pass++) {
-            if (live && mine.y == pass && p != 0.0f) {
+            if (live && mine.y == pass) {
                 float r0 = acc[c[0]], r1 = acc[c[1]], r2 = acc[c[2]], r3 = acc[c[3]];
                 r0 = fmaf(a.x, p, r0); r1 = fmaf(a.y, p, r1); r2 = fmaf(a.z, p, r2); r3 = fmaf(a.w, p, r3);
                 acc[c[0]] = r0; acc[c[1]] = r1; acc[c[2]] = r2; acc[c[3]] = r3;
@@ -213,10 +213,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
                 // which row does flat position k0 + lane belong to?  rows ending inside the chunk
                 // set one bit each; rows that ended before it are counted by a ballot
                 const unsigned e = (unsigned)(pend - k0 - 1);
-                const unsigned endbit = (cgr > 0 && e < 32u) ? (1u << e) : 0u;
-                const unsigned ends = __reduce_or_sync(kFull, endbit);
-                // passes are numbered over the rows that take part in the arithmetic (x != 0)
-                const unsigned ends_act = __reduce_or_sync(kFull, __uint_as_float(m.z) != 0.0f ? endbit : 0u);
+                const unsigned ends = __reduce_or_sync(kFull, (cgr > 0 && e < 32u) ? (1u << e) : 0u);
                 const int i_first = __popc(__ballot_sync(kFull, cgr > 0 && pend <= k0));
                 const int q = k0 + lane;
                 const bool ok = q < total;
@@ -228,9 +225,11 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
                 cp_async16_zfill(ring_v + s * 32 + lane, vals + gs, ok);
                 CI::copy(ring_i + s * 32 + lane, idx, gs, ok);
                 cp_async_commit();
-                ring_m[s * 32 + lane] = make_uint2(x_i, (uint32_t)__popc(ends_act & lt));
+                // row slot inside the chunk = rows that ended before this lane; passes = slots in use
+                ring_m[s * 32 + lane] = make_uint2(x_i, (uint32_t)__popc(ends & lt));
                 const int n_lanes = min(32, total - k0);
-                if (lane == 0) sinfo[s] = make_uint2((uint32_t)n_lanes, (uint32_t)__popc(ends_act) + 1u);
+                const unsigned used = n_lanes == 32 ? ends : (ends & ((1u << n_lanes) - 1u));
+                if (lane == 0) sinfo[s] = make_uint2((uint32_t)n_lanes, (uint32_t)__popc(used & ~(1u << (n_lanes - 1))) + 1u);
             }
         }
     };
