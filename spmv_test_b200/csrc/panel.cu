@@ -161,10 +161,9 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
             const uint4 m = list[r];
 #pragma unroll 1
             for (uint32_t g = m.x; g < m.y; g += 32) {
-                const int s = it & (kStages - 1);
+                const int s = it++ & (kStages - 1);
                 cp_async_wait<kStages - 1>();             // the oldest group (slot s) has landed
-                if (it >= kStages) retire(s);             // (the first kStages slots start empty)
-                it++;
+                retire(s);
                 const uint32_t gg = g + lane;
                 const bool ok = gg < m.y;
                 const uint32_t gs = ok ? gg : g;
@@ -189,7 +188,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         const float p = __uint_as_float(mine.x);
         const bool live = lane < info.x;
         for (uint32_t pass = 0; pass < info.y; pass++) {
-            if (live && mine.y == pass) {
+            if (live && mine.y == pass && p != 0.0f) {
                 float r0 = acc[c[0]], r1 = acc[c[1]], r2 = acc[c[2]], r3 = acc[c[3]];
                 r0 = fmaf(a.x, p, r0); r1 = fmaf(a.y, p, r1); r2 = fmaf(a.z, p, r2); r3 = fmaf(a.w, p, r3);
                 acc[c[0]] = r0; acc[c[1]] = r1; acc[c[2]] = r2; acc[c[3]] = r3;
@@ -206,14 +205,16 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
             const int total = __shfl_sync(kFull, pend, 31);
 #pragma unroll 1
             for (int k0 = 0; k0 < total; k0 += 32) {
-                const int s = it & (kStages - 1);
+                const int s = it++ & (kStages - 1);
                 cp_async_wait<kStages - 1>();
-                if (it >= kStages) retire_mr(s);
-                it++;
+                retire_mr(s);
                 // which row does flat position k0 + lane belong to?  rows ending inside the chunk
                 // set one bit each; rows that ended before it are counted by a ballot
                 const unsigned e = (unsigned)(pend - k0 - 1);
-                const unsigned ends = __reduce_or_sync(kFull, (cgr > 0 && e < 32u) ? (1u << e) : 0u);
+                const unsigned endbit = (cgr > 0 && e < 32u) ? (1u << e) : 0u;
+                const unsigned ends = __reduce_or_sync(kFull, endbit);
+                // passes are numbered over the rows that take part in the arithmetic (x != 0)
+                const unsigned ends_act = __reduce_or_sync(kFull, __uint_as_float(m.z) != 0.0f ? endbit : 0u);
                 const int i_first = __popc(__ballot_sync(kFull, cgr > 0 && pend <= k0));
                 const int q = k0 + lane;
                 const bool ok = q < total;
@@ -225,11 +226,9 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
                 cp_async16_zfill(ring_v + s * 32 + lane, vals + gs, ok);
                 CI::copy(ring_i + s * 32 + lane, idx, gs, ok);
                 cp_async_commit();
-                // row slot inside the chunk = rows that ended before this lane; passes = slots in use
-                ring_m[s * 32 + lane] = make_uint2(x_i, (uint32_t)__popc(ends & lt));
+                ring_m[s * 32 + lane] = make_uint2(x_i, (uint32_t)__popc(ends_act & lt));
                 const int n_lanes = min(32, total - k0);
-                const unsigned used = n_lanes == 32 ? ends : (ends & ((1u << n_lanes) - 1u));
-                if (lane == 0) sinfo[s] = make_uint2((uint32_t)n_lanes, (uint32_t)__popc(used & ~(1u << (n_lanes - 1))) + 1u);
+                if (lane == 0) sinfo[s] = make_uint2((uint32_t)n_lanes, (uint32_t)__popc(ends_act) + 1u);
             }
         }
     };
@@ -294,13 +293,9 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         SPMV_STAMP(wg, 2);
         cp_async_wait<0>();
         SPMV_STAMP(wg, 3);
-        {
-            const int pending = min(it, kStages);         // slots that hold a chunk: the last `pending` issued
 #pragma unroll 1
-            for (int k = it - pending; k < it; k++) {
-                if (MR) retire_mr(k & (kStages - 1)); else retire(k & (kStages - 1));
-            }
-            it = 0;                                       // the next piece starts with an empty ring
+        for (int k = 0; k < kStages; k++) {
+            if (MR) retire_mr(it++ & (kStages - 1)); else retire(it++ & (kStages - 1));
         }
         SPMV_STAMP(wg, 4);
 
