@@ -34,10 +34,16 @@ namespace spmv {
 
 namespace {
 
-constexpr int kPanelMaxWarps = 8;
+#ifndef SPMV_PANEL_WARPS
+#define SPMV_PANEL_WARPS 8
+#endif
+constexpr int kPanelMaxWarps = SPMV_PANEL_WARPS;
 constexpr int kPanelThreads = kPanelMaxWarps * 32;   // launch bound; the CTA size is a plan parameter
 // chunks in flight per warp (cp.async groups)
-constexpr int kRingStages = 8;
+#ifndef SPMV_PANEL_STAGES
+#define SPMV_PANEL_STAGES 8
+#endif
+constexpr int kRingStages = SPMV_PANEL_STAGES;
 
 template <int IDXB> struct ColIdx;
 template <> struct ColIdx<8> {
@@ -389,7 +395,7 @@ int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o)
     const int smem_cap = p->max_smem_optin > 0 ? p->max_smem_optin : 227 * 1024;
     const int per_warp = d.multirow ? (h.index_bits == 8 ? warp_smem_bytes<8, kRingStages, true>(h.slab_cols) : warp_smem_bytes<16, kRingStages, true>(h.slab_cols))
                                     : (h.index_bits == 8 ? warp_smem_bytes<8, kRingStages, false>(h.slab_cols) : warp_smem_bytes<16, kRingStages, false>(h.slab_cols));
-    int warps = 8;
+    int warps = kPanelMaxWarps;
     if (o && o->warps_per_col > 0) {
         warps = 1;
         while (warps * 2 <= std::min(kPanelMaxWarps, o->warps_per_col)) warps *= 2;   // power of two

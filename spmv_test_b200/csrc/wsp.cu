@@ -193,7 +193,10 @@ wsp_merged_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ id
 // FIFO, independent of register and scoreboard limits), partial chunks are zero-filled,
 // x is gathered from shared memory.  The packer
 // deals each chunk's entries so that the 32 lanes' gathers fall into distinct banks.
-constexpr int kRingStages = 8;
+#ifndef SPMV_WSP_STAGES
+#define SPMV_WSP_STAGES 8
+#endif
+constexpr int kRingStages = SPMV_WSP_STAGES;
 constexpr int kRingWarps = 8;
 
 template <typename IdxVec> struct RingCopy;
