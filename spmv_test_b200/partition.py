@@ -11,6 +11,7 @@ which inject the local compute since the product has no CPU path).
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -71,11 +72,13 @@ class ShardedSgemv:
             grp = group if group is not None else dist.group.WORLD
             self.hdl = symm.rendezvous(self.y_sym, grp)
             self.ptrs = [int(q) for q in self.hdl.buffer_ptrs]
+            # NVSwitch multicast alias of the buffers (NVLS): 0 when the allocation has none
             mc = 0
             try:
-                if self.hdl.has_multicast_support(self.device.type, self.device.index or 0):
-                    mc = int(self.hdl.multicast_ptr)
+                mc = int(self.hdl.multicast_ptr or 0)
             except Exception:
+                mc = 0
+            if os.environ.get("SPMV_NO_MULTICAST"):
                 mc = 0
             self.multicast = mc
             self.flip = 0
