@@ -169,8 +169,9 @@ SPMV_API int spmv_run(spmv_plan_t *plan, const float *d_x, float *d_y, void *str
 /*
  * Batched (multi-vector) form, SURVEY section 8f-2: Y[b] = X[b] * A for b < batch, X row-major
  * batch x M (row stride ldx), Y row-major batch x N (row stride ldy, multiple of 4), device
- * pointers.  Weight-sparse plans stream A once per group of 4 (or 2) vectors with all of them in
- * shared memory, so A's bytes are reused; every other case runs the vectors one after the other.
+ * pointers.  wsp plans stream A once per group of 4 (or 2) vectors with all of them in shared
+ * memory, asp plans stream a row once if any of the 4 (or 2) vectors is active there, so A's bytes
+ * are reused; awsp / tcsr plans run the vectors one after the other.
  * Each Y[b] is bit-identical to spmv_run on X[b].
  */
 SPMV_API int spmv_run_batch(spmv_plan_t *plan, int batch, const float *d_X, int64_t ldx, float *d_Y, int64_t ldy,

@@ -27,19 +27,24 @@ namespace {
 #endif
 constexpr int kAspThreads = SPMV_ASP_THREADS;
 constexpr int kAspTile = kAspThreads * 4;     // output columns per CTA
+constexpr int kAspMaxBatch = 4;               // vectors per batched pass
 constexpr int kAspChunk = 1024;               // rows compacted per pass
 #ifndef SPMV_ASP_STAGES
 #define SPMV_ASP_STAGES 16
 #endif
 constexpr int kAspStages = SPMV_ASP_STAGES; // rows in flight per warp
 
+// B > 1: batched form — B activation vectors x[b] (row stride ldx) against the
+// same A: a row is streamed once if ANY vector is active there and used for all of them (a vector
+// with x[b][row] == 0 adds an exact zero), so every y[b] is bit-identical to a single-vector call.
+template <int B>
 __global__ void __launch_bounds__(kAspThreads)
 asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ x, const YDst yd,
            float *__restrict__ partial, unsigned *__restrict__ tickets, int M, int N, int rows_per_split,
-           int splits)
+           int splits, long long ldx, long long ldy)
 {
     __shared__ __align__(16) int rows_s[kAspChunk];
-    __shared__ float xs_s[kAspChunk];
+    __shared__ float xs_s[B * kAspChunk];
     __shared__ int wcnt[kAspThreads / 32];
     __shared__ int last_flag;
     extern __shared__ __align__(16) float4 ring_all[];    // (kAspThreads / 32) * kAspStages * 32
@@ -53,18 +58,25 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
     const float *Ac = A + c0;
     float4 *ring = ring_all + warp * kAspStages * 32;
 
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc[B];
+#pragma unroll
+    for (int b = 0; b < B; b++) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r0 = r_begin; r0 < r_end; r0 += kAspChunk) {
         // ---- compaction of x[r0 .. r0+chunk): warp w takes a contiguous quarter ----------------
         constexpr int kSpan = kAspChunk / (kAspThreads / 32);   // 256 rows per warp
         constexpr int kSteps = kSpan / 32;                      // 8
-        float xr[kSteps]; unsigned bal[kSteps];
+        float xr[B][kSteps]; unsigned bal[kSteps];
         int cnt = 0;
 #pragma unroll
         for (int k = 0; k < kSteps; k++) {
             const int row = r0 + warp * kSpan + k * 32 + lane;
-            xr[k] = row < r_end ? __ldg(x + row) : 0.0f;
-            bal[k] = __ballot_sync(kFull, xr[k] != 0.0f);
+            bool any = false;
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                xr[b][k] = row < r_end ? __ldg(x + b * ldx + row) : 0.0f;
+                any = any || xr[b][k] != 0.0f;
+            }
+            bal[k] = __ballot_sync(kFull, any);
             cnt += __popc(bal[k]);
         }
         __syncthreads();                                  // previous chunk's list fully consumed
@@ -80,10 +92,11 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
         const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
         for (int k = 0; k < kSteps; k++) {
-            if (xr[k] != 0.0f) {
+            if (bal[k] & (1u << lane)) {
                 const int pos = base + __popc(bal[k] & lt);
                 rows_s[pos] = r0 + warp * kSpan + k * 32 + lane;
-                xs_s[pos] = xr[k];
+#pragma unroll
+                for (int b = 0; b < B; b++) xs_s[b * kAspChunk + pos] = xr[b][k];
             }
             base += __popc(bal[k]);
         }
@@ -102,9 +115,12 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
             for (int i = 0; i < total; i++) {
                 cp_async_wait<kAspStages - 1>();          // row i has landed
                 const float4 a = ring[(i & (kAspStages - 1)) * 32 + lane];
-                const float xv = xs_s[i];
-                acc.x = fmaf(a.x, xv, acc.x); acc.y = fmaf(a.y, xv, acc.y);
-                acc.z = fmaf(a.z, xv, acc.z); acc.w = fmaf(a.w, xv, acc.w);
+#pragma unroll
+                for (int b = 0; b < B; b++) {
+                    const float xv = xs_s[b * kAspChunk + i];
+                    acc[b].x = fmaf(a.x, xv, acc[b].x); acc[b].y = fmaf(a.y, xv, acc[b].y);
+                    acc[b].z = fmaf(a.z, xv, acc[b].z); acc[b].w = fmaf(a.w, xv, acc[b].w);
+                }
                 issue(i + kAspStages);
             }
             cp_async_wait<0>();
@@ -112,32 +128,57 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
     }
 
     if (splits == 1) {
-        if (col_ok) y_store4(yd, (size_t)c0 >> 2, acc);
+#pragma unroll
+        for (int b = 0; b < B; b++)
+            if (col_ok) y_store4(yd, ((size_t)b * ldy + c0) >> 2, acc[b]);
         return;
     }
     const size_t npad = (size_t)gridDim.x * kAspTile;
-    *reinterpret_cast<float4 *>(partial + (size_t)split * npad + (size_t)tile * kAspTile + tid * 4) = acc;
     const int n_valid = min(kAspTile, N - tile * kAspTile);
+#pragma unroll
+    for (int b = 0; b < B; b++)
+        *reinterpret_cast<float4 *>(partial + ((size_t)b * splits + split) * npad + (size_t)tile * kAspTile + tid * 4) = acc[b];
     __syncthreads();                                      // the row list is dead: reuse it as scratch
-    split_reduce_finish(yd, partial, tickets, tile, splits, kAspTile, n_valid, npad, &last_flag,
-                        reinterpret_cast<float4 *>(rows_s));
+    for (int b = 0; b < B; b++) {
+        YDst yb = yd;
+        for (int k = 0; k < yb.n; k++) yb.p[k] += (size_t)b * ldy;
+        if (yb.mc) yb.mc += (size_t)b * ldy;
+        split_reduce_finish(yb, partial + (size_t)b * splits * npad, tickets + (size_t)b * gridDim.x, tile, splits, kAspTile,
+                            n_valid, npad, &last_flag, reinterpret_cast<float4 *>(rows_s));
+        __syncthreads();
+    }
 }
 
 } // namespace
 
+template <int B>
+static int launch_asp_b(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st, long long ldx, long long ldy)
+{
+    const int smem = (kAspThreads / 32) * kAspStages * 32 * (int)sizeof(float4);
+    static int smem_set[16] = {0};   // static + dynamic shared memory exceeds 48 KB for B = 4: always opt in
+    if (p->device >= 0 && p->device < 16 && smem_set[p->device] < smem) {
+        SPMV_CUDA(cudaFuncSetAttribute(asp_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set[p->device] = smem;
+    }
+    asp_kernel<B><<<p->grid, kAspThreads, smem, st>>>(p->asp.A, (long long)p->asp.ld, d_x, yd, p->partial, p->tickets,
+                                                     (int)p->M, (int)p->N, p->asp.rows_per_split, p->row_splits, ldx, ldy);
+    SPMV_CUDA(cudaGetLastError());
+    return SPMV_OK;
+}
+
 int launch_asp(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st)
 {
     if (p->N == 0) return SPMV_OK;
-    const int smem = (kAspThreads / 32) * kAspStages * 32 * (int)sizeof(float4);
-    static int smem_set[16] = {0};
-    if (smem > 48 * 1024 && p->device >= 0 && p->device < 16 && smem_set[p->device] < smem) {
-        SPMV_CUDA(cudaFuncSetAttribute(asp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        smem_set[p->device] = smem;
-    }
-    asp_kernel<<<p->grid, kAspThreads, smem, st>>>(p->asp.A, (long long)p->asp.ld, d_x, yd, p->partial, p->tickets,
-                                               (int)p->M, (int)p->N, p->asp.rows_per_split, p->row_splits);
-    SPMV_CUDA(cudaGetLastError());
-    return SPMV_OK;
+    return launch_asp_b<1>(p, d_x, yd, st, 0, 0);
+}
+
+// Batched form: B in {2, 4} vectors in one pass over A's rows.
+int launch_asp_batch(spmv_plan *p, const float *d_x, long long ldx, const YDst &yd, long long ldy, int B, cudaStream_t st)
+{
+    if (p->N == 0) return SPMV_OK;
+    if (B == 2) return launch_asp_b<2>(p, d_x, yd, st, ldx, ldy);
+    if (B == 4) return launch_asp_b<4>(p, d_x, yd, st, ldx, ldy);
+    return SPMV_ERR_UNSUPPORTED;
 }
 
 // grid = (ceil(N/512), row splits): a little over two CTAs per SM, all resident at once — every
@@ -162,7 +203,7 @@ int configure_asp(spmv_plan *p, const spmv_options_t *o)
     p->asp.rows_per_split = rps;
     p->row_splits = splits;
     p->grid = dim3((unsigned)std::max(1, p->col_tiles), (unsigned)splits, 1);
-    return alloc_split_scratch(p);
+    return alloc_split_scratch(p, kAspMaxBatch);
 }
 
 } // namespace spmv

@@ -57,15 +57,15 @@ template <class T> static int upload(spmv_plan *p, T **slot, const std::vector<T
     return SPMV_OK;
 }
 
-int alloc_split_scratch(spmv_plan *p)
+int alloc_split_scratch(spmv_plan *p, int copies)
 {
     if (p->row_splits <= 1) return SPMV_OK;
     const size_t npad = (size_t)p->col_tiles * p->tile_width;
-    int rc = dev_alloc(p, &p->partial, npad * p->row_splits, false);
+    int rc = dev_alloc(p, &p->partial, npad * p->row_splits * copies, false);
     if (rc) return rc;
-    rc = dev_alloc(p, &p->tickets, (size_t)p->col_tiles, true);
+    rc = dev_alloc(p, &p->tickets, (size_t)p->col_tiles * copies, true);
     if (rc) return rc;
-    p->scratch_bytes += (int64_t)(npad * p->row_splits * sizeof(float) + (size_t)p->col_tiles * sizeof(unsigned));
+    p->scratch_bytes += (int64_t)((npad * p->row_splits * sizeof(float) + (size_t)p->col_tiles * sizeof(unsigned)) * copies);
     return SPMV_OK;
 }
 
@@ -578,10 +578,11 @@ int spmv_run_batch(spmv_plan_t *p, int batch, const float *d_X, int64_t ldx, flo
         yd.p[0] = d_Y + (size_t)b * ldy; yd.n = 1; yd.mc = nullptr;
         const float *xb = d_X + (size_t)b * ldx;
         int done = 0;
-        if (p->variant == SPMV_WSP && p->N > 0 && p->M > 0) {
+        if ((p->variant == SPMV_WSP || p->variant == SPMV_ASP) && p->N > 0 && p->M > 0) {
             for (int B : {4, 2}) {
                 if (batch - b < B) continue;
-                const int rc = launch_wsp_batch(p, xb, ldx, yd, ldy, B, st);
+                const int rc = p->variant == SPMV_WSP ? launch_wsp_batch(p, xb, ldx, yd, ldy, B, st)
+                                                       : launch_asp_batch(p, xb, ldx, yd, ldy, B, st);
                 if (rc == SPMV_OK) { done = B; break; }
                 if (rc != SPMV_ERR_UNSUPPORTED) return rc;
             }

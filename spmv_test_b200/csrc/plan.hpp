@@ -115,6 +115,7 @@ struct YDst;   // common.cuh: where y goes (one pointer, or every rank's copy in
 int launch_wsp(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
 int launch_wsp_batch(spmv_plan *p, const float *d_x, long long ldx, const YDst &yd, long long ldy, int B, cudaStream_t st);
 int launch_asp(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
+int launch_asp_batch(spmv_plan *p, const float *d_x, long long ldx, const YDst &yd, long long ldy, int B, cudaStream_t st);
 int launch_panel(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
 int launch_compact(const float *d_x, int64_t M, int32_t *d_idx, float *d_val, int32_t *d_count,
                    void *d_scratch, size_t scratch_bytes, cudaStream_t st);
@@ -125,6 +126,6 @@ int configure_asp(spmv_plan *p, const spmv_options_t *o);
 int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o);
 void destroy_wsp_state(spmv_plan *p);
 int clone_wsp_state(const spmv_plan *src, spmv_plan *dst);
-int alloc_split_scratch(spmv_plan *p);   // partial + tickets from row_splits/col_tiles/tile_width
+int alloc_split_scratch(spmv_plan *p, int copies = 1);   // partial + tickets from row_splits/col_tiles/tile_width (x copies)
 int alloc_panel_scratch(spmv_plan *p, size_t partial_floats, size_t tickets);
 } // namespace spmv

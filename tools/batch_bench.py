@@ -17,7 +17,8 @@ cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 M, N, sa, sx = synth.CONFIGS[cfg]
 A = synth.gen_matrix(M, N, sa)
 st = torch.cuda.Stream()
-plan = S.Plan.from_dense("wsp", A)
+variant = sys.argv[2] if len(sys.argv) > 2 else "wsp"
+plan = S.Plan.from_dense(variant, A)
 plans = bench.make_copies(plan)
 for batch in (1, 2, 4, 8):
     X = np.stack([synth.gen_vector(M, sx, seed=10 + b) for b in range(batch)])
@@ -27,5 +28,5 @@ for batch in (1, 2, 4, 8):
     n = len(plans)
     ms = bench.timed_steps(torch, lambda i, cs: plans[i % n].run_batch(dX, dY, cs), 400, 20, st)
     us = ms * 1e3 / 400
-    print(f"wsp {cfg} batch {batch}: {us:8.3f} us per batched call, {us / batch:7.3f} us per vector, "
+    print(f"{variant} {cfg} batch {batch}: {us:8.3f} us per batched call, {us / batch:7.3f} us per vector, "
           f"{alg / (us * 1e-6) / 1e9:8.1f} GB/s effective", flush=True)
