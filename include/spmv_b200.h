@@ -76,7 +76,10 @@ typedef struct spmv_options {
     int32_t  index_bits;     /* wsp: 16 or 32 bit row indices (0 = auto: 16 if M<65536)  */
     int32_t  slab_cols;      /* awsp/tcsr: columns per slab, power of two 256..4096 (0 = auto from density) */
     int32_t  chunk_mode;     /* awsp/tcsr: 0 = auto, 1 = one row per 32-group chunk, 2 = short rows packed into shared chunks */
-    int32_t  reserved[2];
+    int32_t  pack_mode;      /* dense input: 0 = auto, 1 = pack on the host, 2 = pack on the GPU (the dense matrix is
+                                staged in HBM first; needs M*N*4 bytes of spare device memory).  Both give the
+                                same bytes. */
+    int32_t  reserved[1];
 } spmv_options_t;
 
 typedef struct spmv_plan spmv_plan_t;   /* opaque */
@@ -119,6 +122,17 @@ SPMV_API int         spmv_device_count(void);
  */
 SPMV_API int spmv_plan_create_dense(int variant, int64_t M, int64_t N, const float *A, int64_t lda,
                            const spmv_options_t *opts, spmv_plan_t **out);
+
+/*
+ * The same from a dense row-major matrix that is already in DEVICE memory (current device):
+ * count, prefix sum, fill and the in-chunk ordering all run as kernels (the
+ * reference's packers are single-threaded host loops, wsp.cpp:25-37, awsp.cpp:30-46, and every
+ * launcher call pays for them).  The resulting plan is bit-identical to the one
+ * spmv_plan_create_dense builds from the same values.  d_A is only read and can be freed
+ * afterwards (asp keeps its own copy).  Synchronous.
+ */
+SPMV_API int spmv_plan_create_dense_device(int variant, int64_t M, int64_t N, const float *d_A, int64_t lda,
+                                  const spmv_options_t *opts, spmv_plan_t **out);
 
 /*
  * Direct-to-sparse construction for shapes whose dense form cannot exist

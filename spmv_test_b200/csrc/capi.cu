@@ -57,6 +57,11 @@ template <class T> static int upload(spmv_plan *p, T **slot, const std::vector<T
     return SPMV_OK;
 }
 
+int plan_alloc(spmv_plan *p, void **slot, size_t bytes, bool zero)
+{
+    return dev_alloc(p, reinterpret_cast<char **>(slot), bytes, zero);
+}
+
 int alloc_split_scratch(spmv_plan *p, int copies)
 {
     if (p->row_splits <= 1) return SPMV_OK;
@@ -157,6 +162,7 @@ static bool opts_ok(const spmv_options_t *o)
     if (o->row_splits < 0 || o->warps_per_col < 0) return false;
     if (o->index_bits != 0 && o->index_bits != 16 && o->index_bits != 32) return false;
     if (o->chunk_mode < 0 || o->chunk_mode > 2) return false;
+    if (o->pack_mode < 0 || o->pack_mode > 2) return false;
     if (o->slab_cols != 0 && (o->slab_cols < kMinSlabCols || o->slab_cols > kMaxSlabCols || (o->slab_cols & (o->slab_cols - 1))))
         return false;
     return true;
@@ -232,6 +238,51 @@ void spmv_plan_destroy(spmv_plan_t *p)
     delete p;
 }
 
+// Formats from a dense matrix in device memory (pack_dev.cu); asp only copies.
+static int create_from_device(spmv_plan *p, int variant, const float *d_A, int64_t lda, const spmv_options_t *opts)
+{
+    const int64_t M = p->M, N = p->N;
+    int rc;
+    if (variant == SPMV_WSP) {
+        HostWsp w;
+        rc = pack_wsp_device(p, d_A, lda, opts ? opts->index_bits : 0, w);
+        if (!rc) { p->nnz = w.nnz; p->fmt_groups = w.groups; rc = configure_wsp(p, w, opts); }
+    } else if (variant == SPMV_ASP) {
+        p->nnz = M * N;
+        p->asp.ld = N;
+        rc = dev_alloc(p, &p->asp.A, (size_t)M * N, false);
+        if (!rc) {
+            cudaError_t e = cudaMemcpy2D(p->asp.A, (size_t)N * 4, d_A, (size_t)lda * 4, (size_t)N * 4, (size_t)M,
+                                         cudaMemcpyDeviceToDevice);
+            if (e != cudaSuccess) rc = cuda_error(e, "cudaMemcpy2D(A)");
+        }
+        p->device_bytes += M * N * 4;
+        if (!rc) rc = configure_asp(p, opts);
+    } else {
+        HostPanel h;
+        rc = pack_panel_device(p, d_A, lda, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h);
+        if (!rc) {
+            p->nnz = h.nnz; p->fmt_groups = h.groups;
+            rc = configure_panel(p, h, opts);
+            p->row_nnz.swap(h.row_nnz); p->row_groups.swap(h.row_groups); p->row_segs.swap(h.row_segs);
+        }
+    }
+    return rc;
+}
+
+// pack_mode auto: the GPU packers whenever the dense matrix fits next to its formats (the host
+// packers stay for matrices too large to stage, and as the cross-check of the device ones)
+static bool pack_on_device(const spmv_options_t *opts, int variant, int64_t M, int64_t N)
+{
+    if (M <= 0 || N <= 0 || variant == SPMV_ASP) return false;
+    const int mode = opts ? opts->pack_mode : 0;
+    if (mode == 1) return false;
+    if (mode == 2) return true;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
+    return (double)M * (double)N * 4.0 * 3.0 < (double)free_b;
+}
+
 int spmv_plan_create_dense(int variant, int64_t M, int64_t N, const float *A, int64_t lda,
                            const spmv_options_t *opts, spmv_plan_t **out)
 {
@@ -241,8 +292,15 @@ int spmv_plan_create_dense(int variant, int64_t M, int64_t N, const float *A, in
     spmv_plan *p = nullptr;
     int rc = plan_begin(variant, M, N, &p);
     if (rc) return rc;
+    float *staged = nullptr;
     try {
-        if (variant == SPMV_WSP) {
+        if (pack_on_device(opts, variant, M, N)) {
+            cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&staged), (size_t)M * N * 4);
+            if (e == cudaSuccess)
+                e = cudaMemcpy2D(staged, (size_t)N * 4, A, (size_t)lda * 4, (size_t)N * 4, (size_t)M, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) rc = cuda_error(e, "staging the dense matrix");
+            else rc = create_from_device(p, variant, staged, N, opts);
+        } else if (variant == SPMV_WSP) {
             HostWsp w;
             rc = pack_wsp_dense(M, N, A, lda, opts ? opts->index_bits : 0, w);
             if (rc) set_error(rc, "wsp: cannot pack (index width / size limits)");
@@ -264,6 +322,35 @@ int spmv_plan_create_dense(int variant, int64_t M, int64_t N, const float *A, in
             if (rc) set_error(rc, "panel: cannot pack (size limits)");
             else rc = setup_panel(p, h, opts);
         }
+        if (!rc) rc = plan_finish(p);
+    } catch (const std::bad_alloc &) {
+        rc = set_error(SPMV_ERR_NOMEM, "out of host memory while packing");
+    }
+    if (staged) { cudaFree(staged); cudaGetLastError(); }
+    if (rc) { spmv_plan_destroy(p); return rc; }
+    *out = p;
+    return SPMV_OK;
+}
+
+int spmv_plan_create_dense_device(int variant, int64_t M, int64_t N, const float *d_A, int64_t lda,
+                                  const spmv_options_t *opts, spmv_plan_t **out)
+{
+    if (!opts_ok(opts)) return set_error(SPMV_ERR_ARG, "bad spmv_options_t");
+    if (!d_A && M * N > 0) return set_error(SPMV_ERR_ARG, "d_A is null");
+    if (lda < N) return set_error(SPMV_ERR_ARG, "lda %lld < N %lld", (long long)lda, (long long)N);
+    if (M * N > 0) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, d_A) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+            cudaGetLastError();
+            return set_error(SPMV_ERR_ARG, "d_A is not a device pointer");
+        }
+    }
+    if (M <= 0 || N <= 0) return spmv_plan_create_dense(variant, M, N, nullptr, lda, opts, out);   // nothing to pack
+    spmv_plan *p = nullptr;
+    int rc = plan_begin(variant, M, N, &p);
+    if (rc) return rc;
+    try {
+        rc = create_from_device(p, variant, d_A, lda, opts);
         if (!rc) rc = plan_finish(p);
     } catch (const std::bad_alloc &) {
         rc = set_error(SPMV_ERR_NOMEM, "out of host memory while packing");

@@ -11,6 +11,7 @@
 #include <thread>
 
 #include "formats.hpp"
+#include "deal.hpp"
 #include "plan.hpp"
 #include "spmv_b200.h"
 
@@ -39,42 +40,23 @@ static void wsp_finish_layout(HostWsp &w, const std::vector<int64_t> &list_nnz)
     else w.idx32.assign((size_t)(g + 1) * 4, pad);
 }
 
-// Inside a list the order of the entries is free (any fixed order is deterministic), so it is
-// chosen for the kernel's shared-memory gathers of x: within a chunk of 32 groups the 32 lanes
-// gather element e of their group in one instruction, and the entries are dealt so that those
-// row ids fall into distinct banks (row mod 32) as far as the list allows.
+// In-chunk order for the kernel's shared-memory gathers of x (deal.hpp).
 template <class IdxT> static void wsp_bank_deal(HostWsp &w, std::vector<IdxT> &idx)
 {
-    std::vector<int> bucket[32];
-    std::vector<IdxT> oi(128);
-    std::vector<float> ov(128);
+    IdxT oi[128], li[128];
+    float ov[128], lv[128];
     const int64_t L = (int64_t)w.panels * w.N;
     for (int64_t c = 0; c < L; c++)
         for (int64_t c0 = w.colptr[c]; c0 < w.colptr[c + 1]; c0 += 32) {
             const int lanes = (int)std::min<int64_t>(32, w.colptr[c + 1] - c0);
             const size_t first = (size_t)c0 * 4;
             const int count = 4 * lanes;
-            for (auto &b : bucket) b.clear();
-            for (int k = 0; k < count; k++) bucket[idx[first + k] & 31].push_back(k);
-            int order[32];
-            for (int b = 0; b < 32; b++) order[b] = b;
-            std::stable_sort(order, order + 32, [&](int a, int b) { return bucket[a].size() > bucket[b].size(); });
-            int fill[4] = {0, 0, 0, 0};
-            for (int t = 0; t < 32; t++) {
-                int mine[4] = {0, 0, 0, 0};
-                for (int k : bucket[order[t]]) {
-                    int best = -1;
-                    for (int e = 0; e < 4; e++) {
-                        if (fill[e] >= lanes) continue;
-                        if (best < 0 || mine[e] < mine[best] || (mine[e] == mine[best] && fill[e] < fill[best])) best = e;
-                    }
-                    oi[4 * fill[best] + best] = idx[first + k];
-                    ov[4 * fill[best] + best] = w.vals[first + k];
-                    fill[best]++; mine[best]++;
-                }
-            }
-            std::copy(oi.begin(), oi.begin() + count, idx.begin() + first);
-            std::copy(ov.begin(), ov.begin() + count, w.vals.begin() + first);
+            std::copy(idx.begin() + first, idx.begin() + first + count, li);
+            std::copy(w.vals.begin() + first, w.vals.begin() + first + count, lv);
+            deal_chunk(lanes, [&](int k) { return (unsigned)li[k]; },
+                       [&](int slot, int k) { oi[slot] = li[k]; ov[slot] = lv[k]; });
+            std::copy(oi, oi + count, idx.begin() + first);
+            std::copy(ov, ov + count, w.vals.begin() + first);
         }
 }
 
@@ -86,7 +68,7 @@ static void wsp_bank_order(HostWsp &w)
 // Row panels: when x (M floats) does not fit shared memory next to the ring but the lists
 // stay long enough after the cut (>= 32 non-zeros per (panel, column) on average), cut the rows
 // into panels of 12288 (48 KB of x + 48 KB of ring per CTA: two CTAs per SM).
-static void wsp_choose_panels(HostWsp &w, int64_t nnz, int index_bits_opt)
+void wsp_choose_panels(HostWsp &w, int64_t nnz, int index_bits_opt)
 {
     constexpr int64_t kPanelRows = 12288;
     w.panels = 1; w.panel_rows = w.M;
@@ -246,14 +228,10 @@ void pack_slab(int s, int64_t M, bool tiled, int W, int index_bits, int row_bloc
     if (tiled) O.rel.assign((size_t)row_blocks * kTileRows, 0);
     std::vector<uint16_t> cols((size_t)W + 4), ocols((size_t)W);
     std::vector<float> vals((size_t)W + 4), ovals((size_t)W);
-    std::vector<int> bucket_of[32];
 
-    // Inside a segment the order of the entries is free (every column occurs once per row), so
-    // it is chosen for the kernel's shared-memory accumulators: within a chunk of 32 groups the
-    // 32 lanes process element e of their group in the same instruction, and the entries are
-    // dealt so that those columns fall into distinct banks (column mod 32) as far as the row
-    // allows.  Pads carry value 0 and the smallest column ABSENT from the segment: they add an
-    // exact 0 to an accumulator no real entry of this row touches (n % 4 != 0 implies n < W).
+    // In-chunk order for the kernel's shared-memory accumulators (deal.hpp).  Pads carry value 0
+    // and the smallest column ABSENT from the segment: they add an exact 0 to an accumulator no
+    // real entry of this row touches (n % 4 != 0 implies n < W).
     auto emit = [&](int n) {
         const int g = (n + 3) / 4;
         const size_t at = O.vals.size();
@@ -262,27 +240,9 @@ void pack_slab(int s, int64_t M, bool tiled, int W, int index_bits, int row_bloc
         for (int k = n; k < 4 * g; k++) { cols[k] = absent; vals[k] = 0.0f; }
         for (int c0 = 0; c0 < g; c0 += 32) {               // one chunk = up to 32 groups
             const int lanes = std::min(32, g - c0);
-            const int first = 4 * c0, count = 4 * lanes;
-            for (auto &b : bucket_of) b.clear();
-            for (int k = first; k < first + count; k++) bucket_of[cols[k] & 31].push_back(k);
-            int order[32];
-            for (int b = 0; b < 32; b++) order[b] = b;
-            std::stable_sort(order, order + 32, [&](int a, int b) { return bucket_of[a].size() > bucket_of[b].size(); });
-            int fill[4] = {0, 0, 0, 0};                     // entries dealt to element slot e so far
-            for (int t = 0; t < 32; t++) {                  // largest bank first
-                const std::vector<int> &b = bucket_of[order[t]];
-                int mine[4] = {0, 0, 0, 0};                 // this bank's entries per element slot
-                for (int k : b) {
-                    int best = -1;
-                    for (int e = 0; e < 4; e++) {
-                        if (fill[e] >= lanes) continue;
-                        if (best < 0 || mine[e] < mine[best] || (mine[e] == mine[best] && fill[e] < fill[best])) best = e;
-                    }
-                    ocols[first + 4 * fill[best] + best] = cols[k];
-                    ovals[first + 4 * fill[best] + best] = vals[k];
-                    fill[best]++; mine[best]++;
-                }
-            }
+            const int first = 4 * c0;
+            deal_chunk(lanes, [&](int k) { return (unsigned)cols[first + k]; },
+                       [&](int slot, int k) { ocols[first + slot] = cols[first + k]; ovals[first + slot] = vals[first + k]; });
         }
         O.vals.resize(at + (size_t)g * 4);
         std::memcpy(&O.vals[at], ovals.data(), sizeof(float) * (size_t)g * 4);

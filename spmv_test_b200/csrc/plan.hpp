@@ -29,6 +29,7 @@ int pack_panel_dense(int64_t M, int64_t N, const float *A, int64_t lda, bool til
 int pack_panel_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx,
                    const float *values, bool tiled, int slab_cols, HostPanel &P);
 int choose_slab_cols(int64_t M, int64_t N, int64_t nnz);
+void wsp_choose_panels(HostWsp &w, int64_t nnz, int index_bits_opt);   // sets panels, panel_rows, index_bits
 
 struct DevWsp {
     uint32_t *colptr = nullptr;
@@ -128,4 +129,10 @@ void destroy_wsp_state(spmv_plan *p);
 int clone_wsp_state(const spmv_plan *src, spmv_plan *dst);
 int alloc_split_scratch(spmv_plan *p, int copies = 1);   // partial + tickets from row_splits/col_tiles/tile_width (x copies)
 int alloc_panel_scratch(spmv_plan *p, size_t partial_floats, size_t tickets);
+// a device allocation owned by the plan; `slot` must be a pointer member of *p (capi.cu)
+int plan_alloc(spmv_plan *p, void **slot, size_t bytes, bool zero);
+// device packers (pack_dev.cu): dense matrix in HBM -> the plan's device arrays, bit-identical to
+// the host packers; the Host* argument receives only what the geometry setup needs
+int pack_wsp_device(spmv_plan *p, const float *d_A, int64_t lda, int index_bits_opt, HostWsp &w);
+int pack_panel_device(spmv_plan *p, const float *d_A, int64_t lda, bool tiled, int slab_cols_opt, HostPanel &h);
 } // namespace spmv

@@ -14,9 +14,14 @@ import numpy as np
 from ._cabi import LAYOUTS, VARIANTS, Options, PackedDump, PlanInfo, RefPacked, check, lib
 
 
+PACK_MODES = {"auto": 0, "host": 1, "device": 2}
+
+
 def _opts(**kw):
     if not kw:
         return None
+    if isinstance(kw.get("pack_mode"), str):
+        kw["pack_mode"] = PACK_MODES[kw["pack_mode"]]
     o = Options()
     o.struct_size = C.sizeof(Options)
     for k, v in kw.items():
@@ -52,6 +57,21 @@ class Plan:
         p = cls(h.value)
         p._keep = None
         return p
+
+    @classmethod
+    def from_dense_device(cls, variant, A, **opts):
+        """A: 2-D float32 CUDA tensor (row-major, unit column stride) on the current device: the
+        formats are built by the device packers (csrc/pack_dev.cu), bit-identical to from_dense."""
+        if A.dim() != 2 or not A.is_cuda or str(A.dtype) != "torch.float32":
+            raise TypeError("A must be a 2-D float32 CUDA tensor")
+        M, N = A.shape
+        if A.numel() and (A.stride(1) != 1 or A.stride(0) < N):
+            A = A.contiguous()
+        lda = A.stride(0) if A.numel() and M > 1 else max(N, 1)
+        h = C.c_void_p()
+        check(lib().spmv_plan_create_dense_device(VARIANTS[variant], M, N, C.c_void_p(A.data_ptr() if A.numel() else 0),
+                                                  max(lda, N), _opts(**opts), C.byref(h)))
+        return cls(h.value)
 
     @classmethod
     def from_csc(cls, variant, M, N, col_ptr, row_idx, values, **opts):

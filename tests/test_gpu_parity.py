@@ -414,3 +414,79 @@ def test_run_batch_matches_single_vector_calls(S, batch):
         assert dYp[:, :768].cpu().numpy().tobytes() == Y.tobytes() if v == "wsp" else True
         for b in range(batch):
             assert dYp[b, :768].cpu().numpy().tobytes() == p.run_host(X[b]).tobytes()
+
+
+# ---- device packers (csrc/pack_dev.cu) ----------------------------------------------
+DEVICE_PACK_CASES = [
+    # M, N, keep-density of A, options
+    (512, 512, 0.5, {}),
+    (300, 1024, 0.1, {}),
+    (1000, 2048, 0.3, {}),
+    (64, 4096, 0.9, {}),
+    (2048, 256, 0.02, {}),
+    (777, 1536, 0.6, {"slab_cols": 512}),
+    (640, 4096, 0.7, {"slab_cols": 4096}),
+    (1, 32, 1.0, {}),
+    (33, 64, 0.0, {}),
+    (4096, 4096, 0.1, {}),
+]
+
+
+def _plan_file(plan, path):
+    plan.save(path)
+    return path.read_bytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", DEVICE_PACK_CASES, ids=lambda c: f"{c[0]}x{c[1]}@{c[2]}")
+def test_device_packers_match_host_packers(S, tmp_path, case):
+    """The GPU packers (count / scan / fill / deal kernels) build the same bytes as the host
+    packers: plan files are compared byte for byte, and y bit for bit."""
+    import torch
+    M, N, keep, opts = case
+    rng = np.random.default_rng(M * 131 + N)
+    A = rng.uniform(-1, 1, (M, N)).astype(np.float32)
+    A[rng.random((M, N)) >= keep] = 0.0
+    if M > 8 and keep > 0:
+        A[3, 5] = np.float32("nan"); A[4, 6] = -0.0; A[5, :] = 0.0      # NaN is kept, -0.0 is a zero (a14)
+    x = ob.gen_vector(M, 0.5, 7)
+    dA = torch.from_numpy(A).cuda()
+    for v in ("wsp", "awsp", "tcsr", "asp"):
+        o = {k: w for k, w in opts.items() if v in ("awsp", "tcsr")}
+        with S.Plan.from_dense(v, A, pack_mode="host", **o) as ph, \
+             S.Plan.from_dense(v, A, pack_mode="device", **o) as pd, \
+             S.Plan.from_dense_device(v, dA, **o) as pdd:
+            fh = _plan_file(ph, tmp_path / "h.plan")
+            assert _plan_file(pd, tmp_path / "d.plan") == fh, (v, "host A, device packer")
+            assert _plan_file(pdd, tmp_path / "dd.plan") == fh, (v, "device A")
+            ih, idd = ph.info(), pdd.info()
+            assert ih == idd, v
+            assert ph.traffic(x) == pdd.traffic(x), v
+            yh, yd = ph.run_host(x), pdd.run_host(x)
+            assert np.array_equal(yh, yd, equal_nan=True), v
+
+
+@pytest.mark.gpu
+def test_device_packers_options_and_views(S, tmp_path):
+    import torch
+    # 32-bit row ids, a column-slab view with lda > N, and a tall wsp with row panels
+    A = ob.gen_matrix(1024, 2048, 0.7, 91)
+    dA = torch.from_numpy(A).cuda()
+    with S.Plan.from_dense("wsp", A, index_bits=32, pack_mode="host") as ph, S.Plan.from_dense_device("wsp", dA, index_bits=32) as pd:
+        assert _plan_file(ph, tmp_path / "a") == _plan_file(pd, tmp_path / "b")
+    for v in ("wsp", "awsp", "tcsr", "asp"):
+        with S.Plan.from_dense(v, A[:, 512:1280], pack_mode="host") as ph, S.Plan.from_dense_device(v, dA[:, 512:1280]) as pd:
+            assert _plan_file(ph, tmp_path / "a") == _plan_file(pd, tmp_path / "b"), v
+    T = ob.gen_matrix(30000, 64, 0.5, 92)
+    x = ob.gen_vector(30000, 0.5, 93)
+    with S.Plan.from_dense("wsp", T, pack_mode="host") as ph, S.Plan.from_dense_device("wsp", torch.from_numpy(T).cuda()) as pd:
+        assert _plan_file(ph, tmp_path / "a") == _plan_file(pd, tmp_path / "b")
+        assert ph.run_host(x).tobytes() == pd.run_host(x).tobytes()
+    # a host pointer is rejected, as is a bad pack mode
+    with pytest.raises(S.SpmvError):
+        from spmv_test_b200._cabi import lib, check, VARIANTS as V
+        import ctypes as C
+        h = C.c_void_p()
+        check(lib().spmv_plan_create_dense_device(V["awsp"], 1024, 2048, C.c_void_p(A.ctypes.data), 2048, None, C.byref(h)))
+    with pytest.raises(S.SpmvError):
+        S.Plan.from_dense("awsp", A, pack_mode=7)
