@@ -61,6 +61,7 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
     float4 acc[B];
 #pragma unroll
     for (int b = 0; b < B; b++) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pdl_wait();
     for (int r0 = r_begin; r0 < r_end; r0 += kAspChunk) {
         // ---- compaction of x[r0 .. r0+chunk): warp w takes a contiguous quarter ----------------
         constexpr int kSpan = kAspChunk / (kAspThreads / 32);   // 256 rows per warp
@@ -160,9 +161,8 @@ static int launch_asp_b(spmv_plan *p, const float *d_x, const YDst &yd, cudaStre
         SPMV_CUDA(cudaFuncSetAttribute(asp_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         smem_set[p->device] = smem;
     }
-    asp_kernel<B><<<p->grid, kAspThreads, smem, st>>>(p->asp.A, (long long)p->asp.ld, d_x, yd, p->partial, p->tickets,
-                                                     (int)p->M, (int)p->N, p->asp.rows_per_split, p->row_splits, ldx, ldy);
-    SPMV_CUDA(cudaGetLastError());
+    SPMV_CUDA(launch_k(asp_kernel<B>, p->grid, dim3(kAspThreads), smem, st, p->asp.A, (long long)p->asp.ld, d_x, yd, p->partial,
+                       p->tickets, (int)p->M, (int)p->N, p->asp.rows_per_split, p->row_splits, ldx, ldy));
     return SPMV_OK;
 }
 

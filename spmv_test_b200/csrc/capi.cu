@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -17,6 +18,12 @@ __device__ unsigned long long g_trace[kTraceWarps * kTraceSlots];
 #endif
 
 static thread_local char g_err[512] = "";
+
+bool pdl_enabled()
+{
+    static const int on = [] { const char *e = std::getenv("SPMV_PDL"); return e ? std::atoi(e) != 0 : 1; }();
+    return on != 0;
+}
 
 int set_error(int code, const char *fmt, ...)
 {

@@ -118,6 +118,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     SPMV_STAMP(wg, 0);
     SPMV_STAMP_SMID(wg, 8);
 
+    pdl_wait();
     const long long T = (long long)slabs * M, G = gridDim.x;
     const long long u_begin = range_begin(blockIdx.x, T, G), u_end = range_begin(blockIdx.x + 1, T, G);
 
@@ -351,10 +352,8 @@ int launch_variant(spmv_plan *p, const float *x, const YDst &y, cudaStream_t st)
         smem_set[p->device] = p->smem;
     }
     const DevPanel &d = p->panel;
-    k<<<p->grid, p->block, p->smem, st>>>(reinterpret_cast<const float4 *>(d.vals), d.idx, d.off, d.rel, x, y,
-                                         p->partial, p->tickets, (int)p->M, (int)p->N, d.slab_cols,
-                                         d.row_blocks, d.slabs, d.kmax);
-    SPMV_CUDA(cudaGetLastError());
+    SPMV_CUDA(launch_k(k, p->grid, dim3(p->block), p->smem, st, reinterpret_cast<const float4 *>(d.vals), d.idx, d.off, d.rel,
+                       x, y, p->partial, p->tickets, (int)p->M, (int)p->N, d.slab_cols, d.row_blocks, d.slabs, d.kmax));
     return SPMV_OK;
 }
 

@@ -20,6 +20,31 @@ int cuda_error(cudaError_t e, const char *what); // SPMV_ERR_CUDA + message (nev
         if (e_ != cudaSuccess) return ::spmv::cuda_error(e_, #call);           \
     } while (0)
 
+// Programmatic dependent launch.  Every SGEMV kernel is launched with the programmatic stream
+// serialization attribute and executes `griddepcontrol.wait` (common.cuh: pdl_wait) before it reads
+// or writes global memory.  No kernel triggers its dependents early, so the next kernel of a stream
+// (or captured graph) is placed when the previous grid's CTAs have all exited, and its launch and
+// set-up overlap the previous grid's memory flush; after the wait, ordinary stream order holds.
+// Measured on one box, graph replays: wsp c2 23.03 -> 22.42 us, awsp c2 20.53 -> 20.01, asp c2
+// 24.49 -> 23.99, tcsr c3 11.22 -> 10.66.  An early trigger (griddepcontrol.launch_dependents at
+// kernel entry) lets the next grid's CTAs take free slots next to the running ones and unbalances
+// the SMs: asp c2 32.8 us.  SPMV_PDL=0 turns the attribute off (the wait is a no-op then).
+bool pdl_enabled();
+#ifdef __CUDACC__
+template <class... P, class... A>
+inline cudaError_t launch_k(void (*k)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A &&...a)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k, static_cast<P>(a)...);
+}
+#endif
+
 // host packers (pack_host.cpp)
 int pack_wsp_dense(int64_t M, int64_t N, const float *A, int64_t lda, int index_bits, HostWsp &w);
 int pack_wsp_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx,

@@ -150,6 +150,7 @@ wsp_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
            const uint32_t *__restrict__ colptr, const int32_t *__restrict__ cols, int ncols,
            const float *__restrict__ x, const YDst yd, uint32_t M, int x_bulk_ok)
 {
+    pdl_wait();
     wsp_body<IdxVec, T, XS>(vals, idx, colptr, cols, ncols, x, yd, M, x_bulk_ok, blockIdx.x, gridDim.x);
 }
 
@@ -171,6 +172,7 @@ wsp_merged_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ id
                   const uint32_t *__restrict__ colptr, const BinTable tb, const float *__restrict__ x,
                   const YDst yd, uint32_t M)
 {
+    pdl_wait();
     int b = 0;
     while (b + 1 < tb.n && (int)blockIdx.x >= tb.first_cta[b + 1]) b++;
     const int bid = blockIdx.x - tb.first_cta[b], nb = tb.first_cta[b + 1] - tb.first_cta[b];
@@ -231,6 +233,7 @@ wsp_ring_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
     float4 *ring_v = reinterpret_cast<float4 *>(wsm + xs_bytes) + warp * kRingStages * 32;
     IdxVec *ring_i = reinterpret_cast<IdxVec *>(wsm + xs_bytes + kRingWarps * kRingStages * 32 * 16) + warp * kRingStages * 32;
 
+    pdl_wait();
     // x -> shared memory (1-D bulk async copies when aligned), overlapped with the first chunks
     const uint32_t xstride = (uint32_t)xs_bytes / (4u * B);   // floats per vector in shared memory
     const uint32_t m4 = M & ~3u;
@@ -349,6 +352,7 @@ wsp_ring_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
 __global__ void __launch_bounds__(256)
 wsp_combine_kernel(const float *__restrict__ partial, int panels, int n, const YDst yd)
 {
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     float s = partial[c];
@@ -382,10 +386,9 @@ static int launch_one(const spmv_plan *p, const WspBinDev &b, const float *x, co
         SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set[p->device] = (int)smem;
     }
-    k<<<b.grid, kWspBlock, smem, st>>>(reinterpret_cast<const float4 *>(p->wsp.vals),
-                                       reinterpret_cast<const IdxVec *>(p->wsp.idx), p->wsp.colptr, b.cols,
-                                       b.ncols, x, y, (uint32_t)p->M, x_bulk_ok);
-    SPMV_CUDA(cudaGetLastError());
+    SPMV_CUDA(launch_k(k, dim3(b.grid), dim3(kWspBlock), smem, st, reinterpret_cast<const float4 *>(p->wsp.vals),
+                       reinterpret_cast<const IdxVec *>(p->wsp.idx), p->wsp.colptr, b.cols, b.ncols, x, y, (uint32_t)p->M,
+                       x_bulk_ok));
     return SPMV_OK;
 }
 
@@ -418,14 +421,12 @@ static int launch_ring(const spmv_plan *p, const WspBinDev &b, const float *x, c
         smem_set[p->device] = smem;
     }
     const WspState *ws = reinterpret_cast<const WspState *>(p->wsp_state);
-    k<<<dim3(b.grid, ws->panels), kRingWarps * 32, smem, st>>>(
-        reinterpret_cast<const float4 *>(p->wsp.vals), reinterpret_cast<const IdxVec *>(p->wsp.idx), p->wsp.colptr, b.cols,
-        b.ncols, x, y, (uint32_t)p->M, ok, xs_bytes, (uint32_t)ws->panel_rows, (int)p->N, ws->partial, ldx, ldy);
-    SPMV_CUDA(cudaGetLastError());
-    if (ws->panels > 1) {
-        wsp_combine_kernel<<<(unsigned)((p->N + 255) / 256), 256, 0, st>>>(ws->partial, ws->panels, (int)p->N, y);
-        SPMV_CUDA(cudaGetLastError());
-    }
+    SPMV_CUDA(launch_k(k, dim3(b.grid, ws->panels), dim3(kRingWarps * 32), smem, st, reinterpret_cast<const float4 *>(p->wsp.vals),
+                       reinterpret_cast<const IdxVec *>(p->wsp.idx), p->wsp.colptr, b.cols, b.ncols, x, y, (uint32_t)p->M, ok,
+                       xs_bytes, (uint32_t)ws->panel_rows, (int)p->N, ws->partial, ldx, ldy));
+    if (ws->panels > 1)
+        SPMV_CUDA(launch_k(wsp_combine_kernel, dim3((unsigned)((p->N + 255) / 256)), dim3(256), 0, st, ws->partial, ws->panels,
+                           (int)p->N, y));
     return SPMV_OK;
 }
 
@@ -461,12 +462,11 @@ int launch_wsp(spmv_plan *p, const float *d_x, const YDst &d_y, cudaStream_t st)
         }
         tb.first_cta[tb.n] = total;
         if (p->wsp.index_bits == 16)
-            wsp_merged_kernel<uint2><<<total, kWspBlock, 0, st>>>(reinterpret_cast<const float4 *>(p->wsp.vals),
-                reinterpret_cast<const uint2 *>(p->wsp.idx), p->wsp.colptr, tb, d_x, d_y, (uint32_t)p->M);
+            SPMV_CUDA(launch_k(wsp_merged_kernel<uint2>, dim3(total), dim3(kWspBlock), 0, st, reinterpret_cast<const float4 *>(p->wsp.vals),
+                               reinterpret_cast<const uint2 *>(p->wsp.idx), p->wsp.colptr, tb, d_x, d_y, (uint32_t)p->M));
         else
-            wsp_merged_kernel<uint4><<<total, kWspBlock, 0, st>>>(reinterpret_cast<const float4 *>(p->wsp.vals),
-                reinterpret_cast<const uint4 *>(p->wsp.idx), p->wsp.colptr, tb, d_x, d_y, (uint32_t)p->M);
-        SPMV_CUDA(cudaGetLastError());
+            SPMV_CUDA(launch_k(wsp_merged_kernel<uint4>, dim3(total), dim3(kWspBlock), 0, st, reinterpret_cast<const float4 *>(p->wsp.vals),
+                               reinterpret_cast<const uint4 *>(p->wsp.idx), p->wsp.colptr, tb, d_x, d_y, (uint32_t)p->M));
         return SPMV_OK;
     }
     for (const WspBinDev &b : s->bins) {
