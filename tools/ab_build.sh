@@ -9,5 +9,5 @@ cp spmv_test_b200/csrc/* "$D"/
 git show "$C:spmv_test_b200/csrc/$F" > "$D/$F"
 nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Iinclude -I"$D" \
      -Xcompiler -fPIC,-fvisibility=hidden -shared -o "spmv_test_b200/lib/libspmv_b200_$TAG.so" \
-     "$D"/capi.cu "$D"/wsp.cu "$D"/asp.cu "$D"/panel.cu "$D"/compact.cu "$D"/pack_host.cpp -cudart static
+     "$D"/capi.cu "$D"/wsp.cu "$D"/asp.cu "$D"/panel.cu "$D"/compact.cu "$D"/pack_dev.cu "$D"/pack_host.cpp -cudart static
 rm -rf "$D"
