@@ -352,6 +352,9 @@ int choose_slab_cols(int64_t M, int64_t N, int64_t nnz)
     const double density = (double)nnz / ((double)M * (double)N);
     int w = kMinSlabCols;
     while (w < kMaxSlabCols && w * density < 300.0) w <<= 1;
+    // segments that stay short even at the widest slab (under 12 groups: the kernel's multi-row
+    // mode, bound by latency rather than bytes): 2048 columns, so that two CTAs fit per SM
+    if (w == kMaxSlabCols && w * density < 48.0) w = 2048;
     const int64_t row_blocks = (M + kTileRows - 1) / kTileRows;
     while (w > kMinSlabCols && ((N + w - 1) / w) * row_blocks < 1024) w >>= 1;
     // and at least ~10 slabs: the kernel's CTAs are spread over the slabs, and the last CTA of

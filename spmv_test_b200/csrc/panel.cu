@@ -44,6 +44,11 @@ constexpr int kPanelThreads = kPanelMaxWarps * 32;   // launch bound; the CTA si
 #define SPMV_PANEL_STAGES 8
 #endif
 constexpr int kRingStages = SPMV_PANEL_STAGES;
+// Multi-row mode is bound by the pass-by-pass retire latency, not by bytes in flight: a 4-deep ring
+// leaves room for a second CTA per SM at 2048-column slabs (config-5 slab: 182.5 us with 8 warps per
+// SM, 160.6 us with 16; profiles/r01_notes.md)
+constexpr int kMrStages = 4;
+template <bool MR> constexpr int stages_of() { return MR ? kMrStages : kRingStages; }
 
 template <int IDXB> struct ColIdx;
 template <> struct ColIdx<8> {
@@ -345,7 +350,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
 template <int IDXB, bool TILED, bool MR>
 int launch_variant(spmv_plan *p, const float *x, const YDst &y, cudaStream_t st)
 {
-    auto k = panel_kernel<IDXB, TILED, MR, kRingStages>;
+    auto k = panel_kernel<IDXB, TILED, MR, stages_of<MR>()>;
     static int smem_set[16] = {0};                        // per device: largest dynamic smem opted in so far
     if (p->smem > 48 * 1024 && p->device >= 0 && p->device < 16 && smem_set[p->device] < p->smem) {
         SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem));
@@ -392,7 +397,7 @@ int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o)
     if (o && o->chunk_mode == 1) d.multirow = false;
     if (o && o->chunk_mode == 2) d.multirow = true;
     const int smem_cap = p->max_smem_optin > 0 ? p->max_smem_optin : 227 * 1024;
-    const int per_warp = d.multirow ? (h.index_bits == 8 ? warp_smem_bytes<8, kRingStages, true>(h.slab_cols) : warp_smem_bytes<16, kRingStages, true>(h.slab_cols))
+    const int per_warp = d.multirow ? (h.index_bits == 8 ? warp_smem_bytes<8, kMrStages, true>(h.slab_cols) : warp_smem_bytes<16, kMrStages, true>(h.slab_cols))
                                     : (h.index_bits == 8 ? warp_smem_bytes<8, kRingStages, false>(h.slab_cols) : warp_smem_bytes<16, kRingStages, false>(h.slab_cols));
     int warps = kPanelMaxWarps;
     if (o && o->warps_per_col > 0) {

@@ -99,8 +99,8 @@ def test_panel_slab_auto_from_density():
     wide = S.pack_dump("awsp", ob.gen_matrix(4096, 8192, 0.99, 2))      # few slabs / work units: narrowed
     assert wide.slab_cols == 512 and wide.index_bits == 16
     from spmv_test_b200 import synth
-    cp, ri, va = synth.bernoulli_csc(32768, 65536, 0.01, 9)               # config-5 family: widest slabs
-    assert S.pack_dump("awsp", csc=(cp, ri, va), shape=(32768, 65536)).slab_cols == 4096
+    cp, ri, va = synth.bernoulli_csc(32768, 65536, 0.01, 9)               # config-5 family: short segments even at
+    assert S.pack_dump("awsp", csc=(cp, ri, va), shape=(32768, 65536)).slab_cols == 2048   # 4096 -> 2048 (two CTAs per SM)
 
 
 @pytest.mark.parametrize("M,N,sa", CASES)
