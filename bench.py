@@ -280,21 +280,28 @@ def workload_config(cfg, variant, l2):
                 "M": 4096, "N": 14336, "weight_sparsity": 0.7, "activation_sparsity": 0.5, "variant": variant,
                 "l2": l2}
     return {"workload": "BASELINE config 5 family (weak scaling): per GPU a 131072-column slab of A "
-                        "(65536 rows, 99% sparse, built in sparse form), x 50% activation-sparse, awsp + NCCL "
-                        "all-gather of Y; 8 GPUs = 65536x1048576",
+                        "(65536 rows, 99% sparse, built in sparse form), x 50% activation-sparse, awsp (lane-owned "
+                        "blocks, chunk_mode 3) + all-gather of Y; 8 GPUs = 65536x1048576",
             "M": C5_M, "N_per_gpu": C5_SLAB_N, "weight_sparsity": 0.99, "activation_sparsity": C5_SX,
             "variant": variant, "l2": l2}
 
 
 # ------------------------------------------------------------------------------------------------
-def slab_unit(torch, S, synth, rank, steps, warmup, stream):
+# Config 5 (1 % dense, half of the activations non-zero) runs on the lane-owned block form of the awsp
+# format (chunk_mode 3: every stored non-zero is read, x is a multiplier, one pass per chunk); the
+# row-addressable multi-row form (chunk_mode 0) is reported beside it on one GPU.
+C5_CHUNK_MODE = 3
+
+
+def slab_unit(torch, S, synth, rank, steps, warmup, stream, chunk_mode=C5_CHUNK_MODE):
     """One GPU's config-5 slab: build, time the kernel alone.  Returns (res, plans, bufs, x)."""
     col_ptr, row_idx, vals = synth.bernoulli_csc(C5_M, C5_SLAB_N, C5_DENSITY, seed=5000 + rank)
     x = synth.gen_vector(C5_M, C5_SX, seed=4321)
 
     def build(v):
-        return S.Plan.from_csc(v, C5_M, C5_SLAB_N, col_ptr, row_idx, vals)
+        return S.Plan.from_csc(v, C5_M, C5_SLAB_N, col_ptr, row_idx, vals, chunk_mode=chunk_mode)
     res, plans, bufs, bytes_ = measure_variant(torch, S, HEADLINE, build, x, steps, warmup, stream)
+    res["chunk_mode"] = chunk_mode
     return res, plans, bufs, x, bytes_
 
 
@@ -418,7 +425,12 @@ def main():
             except Exception as e:
                 extra["batched_wsp"] = {"error": str(e)[:200]}
             r, pl, _, _, _ = slab_unit(torch, S, synth, 0, max(50, args.steps // 10), 5, stream)
-            extra["weak_scaling_unit"] = dict(r, workload="one GPU's config-5 slab (65536x131072, 99% sparse, x 50%), kernel only")
+            extra["weak_scaling_unit"] = dict(r, workload="one GPU's config-5 slab (65536x131072, 99% sparse, x 50%), kernel only, "
+                                                          "lane-owned blocks (chunk_mode 3)")
+            for p in pl:
+                p.close()
+            r, pl, _, _, _ = slab_unit(torch, S, synth, 0, max(50, args.steps // 10), 5, stream, chunk_mode=0)
+            extra["weak_scaling_unit_row_form"] = dict(r, workload="the same slab in the row-addressable multi-row form (chunk_mode 0)")
             for p in pl:
                 p.close()
             # config 4: power-law row lengths, 1M x 1M, wsp (32-bit row ids, x gathered through L2)
@@ -532,7 +544,7 @@ def main():
                          "us_per_step_nccl": round(float(tn[0]) / args.steps * 1e3, 3),
                          "us_kernel_only_rank0": res["us_per_call"]}
         roof_alg, roof_us = alg, res["us_per_call"]
-        roof_kernel = "panel_kernel<16,false,true,16>"
+        roof_kernel = "panel_kernel<16,false,false,4,true> (lane-owned blocks)"
         scaling = "weak"
         traffic = ncu_traffic(f"c5/{HEADLINE}")
 

@@ -75,7 +75,10 @@ typedef struct spmv_options {
     int32_t  warps_per_col;  /* wsp: warps cooperating on one column, 1/2/4/8; awsp/tcsr: warps per CTA (0 = auto) */
     int32_t  index_bits;     /* wsp: 16 or 32 bit row indices (0 = auto: 16 if M<65536)  */
     int32_t  slab_cols;      /* awsp/tcsr: columns per slab, power of two 256..4096 (0 = auto from density) */
-    int32_t  chunk_mode;     /* awsp/tcsr: 0 = auto, 1 = one row per 32-group chunk, 2 = short rows packed into shared chunks */
+    int32_t  chunk_mode;     /* awsp/tcsr: 0 = auto, 1 = one row per 32-group chunk, 2 = short rows packed into shared chunks,
+                                3 = lane-owned blocks: for very sparse matrices (segments of a few non-zeros) whose
+                                activations are mostly non-zero — every stored non-zero is read, x is a multiplier,
+                                and a chunk retires in one pass (host packer only; slab_cols 1024..4096, default 2048) */
     int32_t  pack_mode;      /* dense input: 0 = auto, 1 = pack on the host, 2 = pack on the GPU (the dense matrix is
                                 staged in HBM first; needs M*N*4 bytes of spare device memory).  Both give the
                                 same bytes. */
@@ -247,7 +250,7 @@ SPMV_API int spmv_partition_columns(int64_t N, int parts, int64_t align, const i
  *   SPMV_TCSR       vals, idx, off = tile_off[slabs*(row_blocks+1)], rel[slabs*row_blocks*32]
  */
 typedef struct spmv_packed_dump {
-    int32_t  variant, index_bits, slab_cols, slabs, row_blocks, reserved;
+    int32_t  variant, index_bits, slab_cols, slabs, row_blocks, block_rows /* > 0: lane-owned blocks */;
     int64_t  M, N, nnz, groups;
     float    *vals;  int64_t n_vals;
     void     *idx;   int64_t idx_bytes;

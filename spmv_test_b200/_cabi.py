@@ -52,7 +52,7 @@ class RefPacked(C.Structure):
 
 class PackedDump(C.Structure):
     _fields_ = [("variant", C.c_int32), ("index_bits", C.c_int32), ("slab_cols", C.c_int32), ("slabs", C.c_int32),
-                ("row_blocks", C.c_int32), ("reserved", C.c_int32),
+                ("row_blocks", C.c_int32), ("block_rows", C.c_int32),
                 ("M", C.c_int64), ("N", C.c_int64), ("nnz", C.c_int64), ("groups", C.c_int64),
                 ("vals", C.POINTER(C.c_float)), ("n_vals", C.c_int64),
                 ("idx", C.c_void_p), ("idx_bytes", C.c_int64),

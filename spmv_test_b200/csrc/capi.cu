@@ -168,7 +168,7 @@ static bool opts_ok(const spmv_options_t *o)
     if (o->struct_size != sizeof(spmv_options_t)) return false;
     if (o->row_splits < 0 || o->warps_per_col < 0) return false;
     if (o->index_bits != 0 && o->index_bits != 16 && o->index_bits != 32) return false;
-    if (o->chunk_mode < 0 || o->chunk_mode > 2) return false;
+    if (o->chunk_mode < 0 || o->chunk_mode > 3) return false;
     if (o->pack_mode < 0 || o->pack_mode > 2) return false;
     if (o->slab_cols != 0 && (o->slab_cols < kMinSlabCols || o->slab_cols > kMaxSlabCols || (o->slab_cols & (o->slab_cols - 1))))
         return false;
@@ -283,6 +283,7 @@ static bool pack_on_device(const spmv_options_t *opts, int variant, int64_t M, i
 {
     if (M <= 0 || N <= 0 || variant == SPMV_ASP) return false;
     const int mode = opts ? opts->pack_mode : 0;
+    if (opts && opts->chunk_mode == 3 && variant != SPMV_WSP) return false;   // lane-owned blocks: host packer only
     if (mode == 1) return false;
     if (mode == 2) return true;
     size_t free_b = 0, total_b = 0;
@@ -325,7 +326,8 @@ int spmv_plan_create_dense(int variant, int64_t M, int64_t N, const float *A, in
             if (!rc) rc = configure_asp(p, opts);
         } else {
             HostPanel h;
-            rc = pack_panel_dense(M, N, A, lda, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h);
+            rc = pack_panel_dense(M, N, A, lda, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h,
+                                  opts && opts->chunk_mode == 3);
             if (rc) set_error(rc, "panel: cannot pack (size limits)");
             else rc = setup_panel(p, h, opts);
         }
@@ -353,6 +355,8 @@ int spmv_plan_create_dense_device(int variant, int64_t M, int64_t N, const float
         }
     }
     if (M <= 0 || N <= 0) return spmv_plan_create_dense(variant, M, N, nullptr, lda, opts, out);   // nothing to pack
+    if (opts && opts->chunk_mode == 3 && (variant == SPMV_AWSP || variant == SPMV_TCSR))
+        return set_error(SPMV_ERR_UNSUPPORTED, "lane-owned blocks (chunk_mode 3) are packed on the host: use spmv_plan_create_dense/_csc");
     spmv_plan *p = nullptr;
     int rc = plan_begin(variant, M, N, &p);
     if (rc) return rc;
@@ -388,7 +392,8 @@ int spmv_plan_create_csc(int variant, int64_t M, int64_t N, const int64_t *col_p
             else rc = setup_wsp(p, w, opts);
         } else {
             HostPanel h;
-            rc = pack_panel_csc(M, N, col_ptr, row_idx, values, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h);
+            rc = pack_panel_csc(M, N, col_ptr, row_idx, values, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h,
+                                opts && opts->chunk_mode == 3);
             if (rc) set_error(rc, "panel: cannot pack (row index out of range or size limits)");
             else rc = setup_panel(p, h, opts);
         }
@@ -459,7 +464,8 @@ int spmv_plan_save(const spmv_plan_t *p, const char *path)
         const DevPanel &d = p->panel;
         h.M = p->M; h.N = p->N; h.nnz = p->nnz; h.groups = p->fmt_groups; h.slab_cols = d.slab_cols;
         h.index_bits = d.index_bits; h.slabs = d.slabs; h.row_blocks = d.row_blocks; h.tiled = d.tiled;
-        rc = fetch(h.off, d.off, (size_t)d.slabs * (d.tiled ? d.row_blocks + 1 : p->M + 1));
+        h.block_rows = d.block_rows; h.lob_blocks = d.lob_blocks;
+        rc = fetch(h.off, d.off, (size_t)d.slabs * (d.block_rows > 0 ? d.lob_blocks + 1 : d.tiled ? d.row_blocks + 1 : p->M + 1));
         if (!rc && d.tiled) rc = fetch(h.rel, d.rel, (size_t)d.slabs * d.row_blocks * kTileRows);
         if (!rc) rc = fetch(h.vals, d.vals, (size_t)h.groups * 4);
         if (!rc) rc = d.index_bits == 8 ? fetch(h.idx8, d.idx, (size_t)h.groups * 4) : fetch(h.idx16, d.idx, (size_t)h.groups * 4);
@@ -478,7 +484,7 @@ int spmv_plan_save(const spmv_plan_t *p, const char *path)
         fw.vec(dense);
     } else {
         fw.pod<int64_t>(h.groups); fw.pod<int32_t>(h.slab_cols); fw.pod<int32_t>(h.index_bits); fw.pod<int32_t>(h.slabs);
-        fw.pod<int32_t>(h.row_blocks); fw.pod<int32_t>(h.tiled ? 1 : 0);
+        fw.pod<int32_t>(h.row_blocks); fw.pod<int32_t>(h.tiled ? 1 : 0); fw.pod<int32_t>(h.block_rows);
         fw.vec(h.off); fw.vec(h.rel); fw.vec(h.vals); fw.vec(h.idx8); fw.vec(h.idx16);
         fw.vec(h.row_nnz); fw.vec(h.row_groups); fw.vec(h.row_segs);
     }
@@ -547,15 +553,21 @@ int spmv_plan_load(const char *path, const spmv_options_t *opts, spmv_plan_t **o
             }
         } else if (variant == SPMV_AWSP || variant == SPMV_TCSR) {
             HostPanel h; h.M = M; h.N = N; h.nnz = nnz;
-            int32_t sc = 0, ib = 0, slabs = 0, rb = 0, tiled = 0;
-            fr.pod(h.groups); fr.pod(sc); fr.pod(ib); fr.pod(slabs); fr.pod(rb); fr.pod(tiled);
+            int32_t sc = 0, ib = 0, slabs = 0, rb = 0, tiled = 0, br = 0;
+            fr.pod(h.groups); fr.pod(sc); fr.pod(ib); fr.pod(slabs); fr.pod(rb); fr.pod(tiled); fr.pod(br);
             h.slab_cols = sc; h.index_bits = ib; h.slabs = slabs; h.row_blocks = rb; h.tiled = tiled != 0;
+            const bool lob = br != 0;
+            if (lob) {
+                if (sc < kMinSlabCols || sc > kMaxSlabCols || (sc & (sc - 1)) || br != std::min(kLobMaxBlockRows, (65536 * 32) / sc)) return fail("corrupt panel plan file (blocks)");
+                h.block_rows = br; h.lob_blocks = (int)((M + br - 1) / br);
+            }
             fr.vec(h.off); fr.vec(h.rel); fr.vec(h.vals); fr.vec(h.idx8); fr.vec(h.idx16);
             fr.vec(h.row_nnz); fr.vec(h.row_groups); fr.vec(h.row_segs);
             uint64_t tail = 0; fr.pod(tail);
-            const size_t per_slab = h.tiled ? (size_t)rb + 1 : (size_t)M + 1;
+            const size_t per_slab = lob ? (size_t)h.lob_blocks + 1 : h.tiled ? (size_t)rb + 1 : (size_t)M + 1;
             const bool sane = fr.ok && tail == kFileMagic && (ib == 8 || ib == 16) && sc >= kMinSlabCols && sc <= kMaxSlabCols &&
-                              !(sc & (sc - 1)) && (ib == 8) == (sc == 256) && slabs == (int32_t)((N + sc - 1) / sc) &&
+                              !(sc & (sc - 1)) && (ib == 8) == (sc == 256 && !lob) && !(lob && h.tiled) &&
+                              (!lob || h.groups % 32 == 0) && slabs == (int32_t)((N + sc - 1) / sc) &&
                               rb == (int32_t)((M + kTileRows - 1) / kTileRows) && h.groups >= 0 &&
                               h.off.size() == (size_t)slabs * per_slab && h.vals.size() == (size_t)h.groups * 4 &&
                               (ib == 8 ? h.idx8.size() : h.idx16.size()) == h.vals.size() &&
@@ -565,7 +577,19 @@ int spmv_plan_load(const char *path, const spmv_options_t *opts, spmv_plan_t **o
             if (!sane) return fail("corrupt panel plan file");
             for (size_t i = 0; i + 1 < h.off.size(); i++)
                 if (h.off[i] > h.off[i + 1] || h.off[i + 1] > (uint32_t)h.groups) return fail("corrupt panel plan file (offsets)");
-            if (ib == 16) for (uint16_t v : h.idx16) if (v >= sc) return fail("corrupt panel plan file (column ids)");
+            if (ib == 16 && !lob) for (uint16_t v : h.idx16) if (v >= sc) return fail("corrupt panel plan file (column ids)");
+            if (lob) {                                     // row ids must stay inside the matrix (x is read at block*rows + id)
+                int cb = 0;
+                while ((32 << cb) < sc) cb++;
+                const size_t per = (size_t)h.lob_blocks + 1;
+                for (int sl = 0; sl < slabs; sl++)
+                    for (int b = 0; b < h.lob_blocks; b++) {
+                        if (h.off[sl * per + b] % 32) return fail("corrupt panel plan file (block offsets)");
+                        const int64_t lim = std::min<int64_t>(br, M - (int64_t)b * br);
+                        for (size_t k = (size_t)h.off[sl * per + b] * 4; k < (size_t)h.off[sl * per + b + 1] * 4; k++)
+                            if ((h.idx16[k] >> cb) >= lim) return fail("corrupt panel plan file (row ids)");
+                    }
+            }
             for (int32_t v : h.row_segs) h.nonempty_segments += v;
             fclose(f); f = nullptr;
             rc = plan_begin(variant, M, N, &p);
@@ -628,6 +652,7 @@ int spmv_plan_traffic(const spmv_plan_t *p, const float *x, double *alg_bytes, d
         for (int64_t j = 0; j < p->M; j++)
             if (x[j] != 0.0f) { touched += p->row_nnz[j]; groups += p->row_groups[j]; }
         alg = 8.0 * touched + 4.0 * (N + 1) + vec;
+        if (p->panel.block_rows > 0) groups = p->fmt_groups;   // lane-owned blocks: every group is read, x is a multiplier
         phys = (double)groups * (16.0 + 4.0 * p->panel.index_bits / 8.0) + (double)p->off_bytes + vec + split_io;
     }
     if (alg_bytes) *alg_bytes = alg;

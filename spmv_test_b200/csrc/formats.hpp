@@ -48,9 +48,26 @@ struct HostWsp {
 //         rel[(slab*RB + rb)*32 + r] = first group of row r inside the tile (16-bit)
 //         i.e. a two-level offset: 2 bytes per segment instead of 4.
 // ------------------------------------------------------------------------------------------
+//
+// Lane-owned blocks (chunk_mode 3; very sparse matrices with fairly dense activations, e.g.
+// BASELINE config 5): the multi-row schedule has to retire a chunk one row at a time because two
+// rows may hit the same column.  Here lane l of a warp only ever handles columns congruent to l
+// modulo 32, so no two lanes can meet in an accumulator (and bank = lane: no bank conflicts) and a
+// chunk retires in a single pass whatever rows it mixes.  Rows are cut into blocks of `block_rows`;
+// inside a (slab, block) every lane has its own stream of entries (row ascending), cut into groups
+// of four and padded to the longest lane's length; group (g, lane) is stored at off[block] + 32 g +
+// lane, so a warp's 32 groups are one contiguous 512-byte run:
+//   vals  float4 [groups]     values (pads: 0)
+//   idx   ushort4 [groups]    (row inside the block) << cbits | (column inside the slab) >> 5,
+//                              cbits = log2(slab_cols / 32), block_rows = min(1024, 2^(16 - cbits))
+//   off[slab*(blocks+1) + block]   first group of the block (32-bit, multiple of 32)
+// Every stored non-zero is read whatever x is (x enters as a multiplier), so this form wins when
+// more than about a third of the activations are non-zero.
 constexpr int kTileRows = 32;
 constexpr int kMinSlabCols = 256;
 constexpr int kMaxSlabCols = 4096;
+constexpr int kLobSlabCols = 2048;       // lane-owned blocks: 2048 columns x 1024 rows per block
+constexpr int kLobMaxBlockRows = 1024;   // rows per block: min(this, 2^(16 - cbits))
 
 struct HostPanel {
     int64_t M = 0, N = 0, nnz = 0, groups = 0, nonempty_segments = 0;
@@ -59,6 +76,8 @@ struct HostPanel {
     int slabs = 0;
     int row_blocks = 0;          // ceil(M/32)
     bool tiled = false;          // false: AWSP (per-row offsets), true: TCSR (two-level offsets)
+    int block_rows = 0;          // > 0: lane-owned blocks of this many rows (off is per block)
+    int lob_blocks = 0;          //      ceil(M / block_rows)
     std::vector<uint32_t> off;       // AWSP: slabs*(M+1);  TCSR: slabs*(row_blocks+1)
     std::vector<uint16_t> rel;       // TCSR: slabs*row_blocks*32
     std::vector<float> vals;         // 4*groups

@@ -278,21 +278,77 @@ void pack_slab(int s, int64_t M, bool tiled, int W, int index_bits, int row_bloc
     O.off[(size_t)(tiled ? row_blocks : M)] = (uint32_t)O.groups;
 }
 
+// Lane-owned blocks (formats.hpp): per (slab, block) one stream per lane, padded to the longest.
+template <class Source>
+void pack_slab_lob(int s, int64_t M, int W, int R, Source &src, SlabOut &O, RowStats &st)
+{
+    int cbits = 0;
+    while ((32 << cbits) < W) cbits++;
+    const int64_t NB = (M + R - 1) / R;
+    O.off.assign((size_t)NB + 1, 0);
+    std::vector<uint16_t> cols((size_t)W + 4), li[32];
+    std::vector<float> vals((size_t)W + 4), lv[32];
+    src.begin_slab(s);
+    for (int64_t b = 0; b < NB; b++) {
+        O.off[(size_t)b] = (uint32_t)O.groups;
+        for (int l = 0; l < 32; l++) { li[l].clear(); lv[l].clear(); }
+        const int64_t r1 = std::min<int64_t>(M, (b + 1) * R);
+        for (int64_t row = b * R; row < r1; row++) {
+            const int n = src.get(s, row, cols.data(), vals.data());
+            for (int k = 0; k < n; k++) {
+                const int l = cols[k] & 31;
+                li[l].push_back((uint16_t)(((row - b * R) << cbits) | (cols[k] >> 5)));
+                lv[l].push_back(vals[k]);
+            }
+            if (n) { st.nnz[row] += n; st.groups[row] += (n + 3) / 4; st.segs[row] += 1; O.nnz += n; O.segs++; }
+        }
+        size_t longest = 0;
+        for (int l = 0; l < 32; l++) longest = std::max(longest, li[l].size());
+        const int64_t G = (int64_t)((longest + 3) / 4);    // chunks of this block
+        const size_t at = O.vals.size();
+        O.vals.resize(at + (size_t)G * 128);
+        O.idx16.resize(at + (size_t)G * 128);
+        for (int64_t g = 0; g < G; g++)
+            for (int l = 0; l < 32; l++) {
+                // a pad repeats the lane's last entry with value 0: same accumulator, a row that exists
+                const uint16_t pad = li[l].empty() ? (uint16_t)0 : li[l].back();
+                for (int e = 0; e < 4; e++) {
+                    const size_t k = (size_t)g * 4 + e, o = at + ((size_t)g * 32 + l) * 4 + e;
+                    const bool real = k < li[l].size();
+                    O.vals[o] = real ? lv[l][k] : 0.0f;
+                    O.idx16[o] = real ? li[l][k] : pad;
+                }
+            }
+        O.groups += G * 32;
+        if (O.groups >= (int64_t)UINT32_MAX) { O.rc = SPMV_ERR_UNSUPPORTED; return; }
+    }
+    O.off[(size_t)NB] = (uint32_t)O.groups;
+}
+
 // Slabs are independent, so they are packed by a small pool of host threads (the reference packs
 // on one thread with vector<vector<float>> copies, awsp.cpp:30-46) and concatenated afterwards;
 // the result does not depend on the thread count.
 template <class Source>
-int pack_panel(int64_t M, int64_t N, bool tiled, int W, const Source &proto, HostPanel &P)
+int pack_panel(int64_t M, int64_t N, bool tiled, int W, bool lane_owned, const Source &proto, HostPanel &P)
 {
     if (W < kMinSlabCols || W > kMaxSlabCols || (W & (W - 1))) return SPMV_ERR_ARG;
+    if (lane_owned) tiled = false;
+    if (lane_owned && W < 1024) return SPMV_ERR_ARG;       // blocks of at most 2048 rows (the kernel stages their x slices)
     P.M = M; P.N = N; P.tiled = tiled;
     P.slab_cols = W;
-    P.index_bits = (W == 256) ? 8 : 16;
+    P.index_bits = (W == 256 && !lane_owned) ? 8 : 16;
+    P.block_rows = 0; P.lob_blocks = 0;
+    if (lane_owned) {
+        int cbits = 0;
+        while ((32 << cbits) < W) cbits++;
+        P.block_rows = std::min(kLobMaxBlockRows, 1 << (16 - cbits));
+        P.lob_blocks = (int)((M + P.block_rows - 1) / P.block_rows);
+    }
     P.slabs = (int)((N + W - 1) / W);
     P.row_blocks = (int)((M + kTileRows - 1) / kTileRows);
     P.nnz = 0; P.groups = 0; P.nonempty_segments = 0;
     P.vals.clear(); P.idx8.clear(); P.idx16.clear(); P.rel.clear();
-    const int64_t per_slab = tiled ? (P.row_blocks + 1) : (M + 1);
+    const int64_t per_slab = lane_owned ? (P.lob_blocks + 1) : tiled ? (P.row_blocks + 1) : (M + 1);
 
     int n_threads = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
     if (const char *e = std::getenv("SPMV_PACK_THREADS")) n_threads = std::max(1, std::atoi(e));
@@ -302,8 +358,10 @@ int pack_panel(int64_t M, int64_t N, bool tiled, int W, const Source &proto, Hos
     for (RowStats &st : stats) { st.nnz.assign((size_t)M, 0); st.groups.assign((size_t)M, 0); st.segs.assign((size_t)M, 0); }
     auto worker = [&](int t) {
         Source src = proto;                                // per-thread scratch (CSR(A^T) row buckets)
-        for (int s = t; s < P.slabs; s += n_threads)
-            pack_slab(s, M, tiled, W, P.index_bits, P.row_blocks, src, outs[(size_t)s], stats[(size_t)t]);
+        for (int s = t; s < P.slabs; s += n_threads) {
+            if (lane_owned) pack_slab_lob(s, M, W, P.block_rows, src, outs[(size_t)s], stats[(size_t)t]);
+            else pack_slab(s, M, tiled, W, P.index_bits, P.row_blocks, src, outs[(size_t)s], stats[(size_t)t]);
+        }
     };
     if (n_threads == 1) worker(0);
     else {
@@ -364,8 +422,9 @@ int choose_slab_cols(int64_t M, int64_t N, int64_t nnz)
 }
 
 int pack_panel_dense(int64_t M, int64_t N, const float *A, int64_t lda, bool tiled, int slab_cols,
-                     HostPanel &P)
+                     HostPanel &P, bool lane_owned)
 {
+    if (lane_owned && slab_cols <= 0) slab_cols = kLobSlabCols;
     if (slab_cols <= 0) {
         int64_t nnz = 0;
         for (int64_t j = 0; j < M; j++) {
@@ -375,12 +434,13 @@ int pack_panel_dense(int64_t M, int64_t N, const float *A, int64_t lda, bool til
         slab_cols = choose_slab_cols(M, N, nnz);
     }
     DenseSource src{A, lda, N, slab_cols};
-    return pack_panel(M, N, tiled, slab_cols, src, P);
+    return pack_panel(M, N, tiled, slab_cols, lane_owned, src, P);
 }
 
 int pack_panel_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx,
-                   const float *values, bool tiled, int slab_cols, HostPanel &P)
+                   const float *values, bool tiled, int slab_cols, HostPanel &P, bool lane_owned)
 {
+    if (lane_owned && slab_cols <= 0) slab_cols = kLobSlabCols;
     int64_t nnz = 0;
     for (int64_t k = col_ptr[0]; k < col_ptr[N]; k++) {
         if (row_idx[k] < 0 || row_idx[k] >= M) return SPMV_ERR_ARG;
@@ -388,7 +448,7 @@ int pack_panel_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *
     }
     if (slab_cols <= 0) slab_cols = choose_slab_cols(M, N, nnz);
     CscSource src{col_ptr, row_idx, values, M, N, slab_cols, {}, {}, {}};
-    return pack_panel(M, N, tiled, slab_cols, src, P);
+    return pack_panel(M, N, tiled, slab_cols, lane_owned, src, P);
 }
 
 } // namespace spmv
@@ -615,6 +675,7 @@ void dump_panel(const spmv::HostPanel &h, int variant, spmv_packed_dump_t *o)
 {
     o->variant = variant; o->index_bits = h.index_bits; o->slab_cols = h.slab_cols; o->slabs = h.slabs;
     o->row_blocks = h.row_blocks; o->M = h.M; o->N = h.N; o->nnz = h.nnz; o->groups = h.groups;
+    o->block_rows = h.block_rows;
     o->vals = dup_vec(h.vals); o->n_vals = (int64_t)h.vals.size();
     if (h.index_bits == 8) { o->idx = dup_vec(h.idx8); o->idx_bytes = (int64_t)h.idx8.size(); }
     else { o->idx = dup_vec(h.idx16); o->idx_bytes = (int64_t)h.idx16.size() * 2; }
@@ -646,7 +707,8 @@ extern "C" int spmv_pack_dump_dense(int variant, int64_t M, int64_t N, const flo
             if (!rc) dump_wsp(w, out);
         } else {
             spmv::HostPanel h;
-            rc = spmv::pack_panel_dense(M, N, A, lda, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h);
+            rc = spmv::pack_panel_dense(M, N, A, lda, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h,
+                                        opts && opts->chunk_mode == 3);
             if (!rc) dump_panel(h, variant, out);
         }
     } catch (const std::bad_alloc &) { rc = SPMV_ERR_NOMEM; }
@@ -668,7 +730,8 @@ extern "C" int spmv_pack_dump_csc(int variant, int64_t M, int64_t N, const int64
             if (!rc) dump_wsp(w, out);
         } else {
             spmv::HostPanel h;
-            rc = spmv::pack_panel_csc(M, N, col_ptr, row_idx, values, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h);
+            rc = spmv::pack_panel_csc(M, N, col_ptr, row_idx, values, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h,
+                                      opts && opts->chunk_mode == 3);
             if (!rc) dump_panel(h, variant, out);
         }
     } catch (const std::bad_alloc &) { rc = SPMV_ERR_NOMEM; }

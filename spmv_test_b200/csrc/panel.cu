@@ -48,7 +48,11 @@ constexpr int kRingStages = SPMV_PANEL_STAGES;
 // leaves room for a second CTA per SM at 2048-column slabs (config-5 slab: 182.5 us with 8 warps per
 // SM, 160.6 us with 16; profiles/r01_notes.md)
 constexpr int kMrStages = 4;
-template <bool MR> constexpr int stages_of() { return MR ? kMrStages : kRingStages; }
+#ifndef SPMV_LOB_STAGES
+#define SPMV_LOB_STAGES 4
+#endif
+constexpr int kLobStages = SPMV_LOB_STAGES;    // lane-owned blocks: room for the three x buffers next to two CTAs per SM
+template <bool MR, bool LOB = false> constexpr int stages_of() { return LOB ? kLobStages : MR ? kMrStages : kRingStages; }
 
 template <int IDXB> struct ColIdx;
 template <> struct ColIdx<8> {
@@ -80,9 +84,9 @@ template <> struct ColIdx<16> {
 //                         [slot info][multi-row mode: per-lane (x, row slot) ring]
 constexpr int kListCap = 128;              // rows a warp can take from one metadata batch
 constexpr int kMetaBatch = 8;              // 32-row blocks of metadata fetched together
-template <int IDXB, int kStages, bool MR> __host__ __device__ constexpr int warp_smem_bytes(int W)
+template <int IDXB, int kStages, bool MR, bool LOB = false> __host__ __device__ constexpr int warp_smem_bytes(int W)
 {
-    return W * 4 + kStages * 32 * 16 + kStages * 32 * (IDXB == 8 ? 4 : 8) + kListCap * 16 + kStages * 8 +
+    return W * 4 + kStages * 32 * 16 + kStages * 32 * (IDXB == 8 ? 4 : 8) + (LOB ? 0 : kListCap * 16) + kStages * 8 +
            (MR ? kStages * 32 * 8 : 0);
 }
 
@@ -96,12 +100,15 @@ template <int IDXB, int kStages, bool MR> __host__ __device__ constexpr int warp
 __device__ __forceinline__ long long range_begin(long long c, long long T, long long G) { return c * T / G; }
 __device__ __forceinline__ long long cta_of_unit(long long u, long long T, long long G) { return ((u + 1) * G - 1) / T; }
 
-template <int IDXB, bool TILED, bool MR, int kStages>
+// LOB: lane-owned blocks (formats.hpp) — the units of the flat sequence are (slab, block) pairs
+// (`units` = blocks per slab), lane l owns the columns congruent to l modulo 32.
+template <int IDXB, bool TILED, bool MR, int kStages, bool LOB = false>
 __global__ void __launch_bounds__(kPanelThreads)
 panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
              const uint32_t *__restrict__ off, const uint16_t *__restrict__ rel,
              const float *__restrict__ x, const YDst yd, float *__restrict__ partial,
-             unsigned *__restrict__ tickets, int M, int N, int W, int row_blocks, int slabs, int kmax)
+             unsigned *__restrict__ tickets, int M, int N, int W, int row_blocks, int slabs, int kmax,
+             int units, int block_rows, int cbits)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int last_flag;
@@ -111,12 +118,12 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_warps = blockDim.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes<IDXB, kStages, MR>(W);
+    unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes<IDXB, kStages, MR, LOB>(W);
     float *acc = reinterpret_cast<float *>(wbase);
     float4 *ring_v = reinterpret_cast<float4 *>(wbase + (size_t)W * 4);
     IVec *ring_i = reinterpret_cast<IVec *>(wbase + (size_t)W * 4 + kStages * 32 * 16);
     uint4 *list = reinterpret_cast<uint4 *>(wbase + (size_t)W * 4 + kStages * 32 * 16 + kStages * 32 * sizeof(IVec));
-    uint2 *sinfo = reinterpret_cast<uint2 *>(list + kListCap);   // per ring slot: (valid lanes, x of the row | passes)
+    uint2 *sinfo = reinterpret_cast<uint2 *>(list + (LOB ? 0 : kListCap));   // per ring slot: (valid lanes, x of the row | passes)
     uint2 *ring_m = sinfo + kStages;                             // MR: per lane (x of its row, row slot in the chunk)
     const int wg = blockIdx.x * n_warps + warp;           // trace id
     (void)wg;
@@ -124,7 +131,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     SPMV_STAMP_SMID(wg, 8);
 
     pdl_wait();
-    const long long T = (long long)slabs * M, G = gridDim.x;
+    const long long T = (long long)slabs * units, G = gridDim.x;
     const long long u_begin = range_begin(blockIdx.x, T, G), u_end = range_begin(blockIdx.x + 1, T, G);
 
     // ---- metadata of one 32-row block of a slab: lane = row ---------------------------------------
@@ -244,11 +251,99 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
             }
         }
     };
+    // Lane-owned blocks: a chunk is 32 groups of one (slab, block); lane l's four entries belong to
+    // columns 32*c + l, so lanes never meet in an accumulator and the chunk retires in one pass with
+    // no votes, no predicates and no bank conflicts.  x enters as a multiplier: the CTA keeps the x
+    // slices of three consecutive blocks in shared memory (the block being streamed, the one before
+    // it, whose last chunks may still sit in a ring, and the next one, fetched into registers while
+    // the current block streams).  All warps of the CTA walk the same blocks, each taking every
+    // n_warps-th chunk.
+    float *xbuf = reinterpret_cast<float *>(smem_raw + (size_t)n_warps * warp_smem_bytes<IDXB, kStages, MR, LOB>(W));
+    auto retire_lob = [&](int s) {
+        const uint2 info = sinfo[s];                      // (live, x buffer of the block)
+        if (!info.x) return;
+        const float4 a = ring_v[s * 32 + lane];
+        uint32_t c[4];
+        CI::unpack(ring_i[s * 32 + lane], c);
+        const float *xb = xbuf + info.y;
+        const uint32_t cmask = (1u << cbits) - 1u;
+        const float p0 = xb[c[0] >> cbits], p1 = xb[c[1] >> cbits], p2 = xb[c[2] >> cbits], p3 = xb[c[3] >> cbits];
+        float *al = acc + lane;
+        // one after the other: two entries of a group may share a column (different rows)
+        { float *q = al + ((c[0] & cmask) << 5); *q = fmaf(a.x, p0, *q); }
+        { float *q = al + ((c[1] & cmask) << 5); *q = fmaf(a.y, p1, *q); }
+        { float *q = al + ((c[2] & cmask) << 5); *q = fmaf(a.z, p2, *q); }
+        { float *q = al + ((c[3] & cmask) << 5); *q = fmaf(a.w, p3, *q); }
+    };
+    constexpr int kXPerThread = kLobMaxBlockRows / kPanelThreads;   // block_rows <= 1024, 256 threads
+    auto run_blocks = [&](int slab, int blk_a, int blk_b) {
+        const uint32_t *ob = off + (size_t)slab * (units + 1);
+        uint32_t g1 = __ldg(ob + blk_a), g2 = __ldg(ob + blk_a + 1);
+        float nx[kXPerThread];
+        auto fetch_x = [&](int blk) {                     // this thread's share of a block's x slice -> registers
+#pragma unroll
+            for (int k = 0; k < kXPerThread; k++) {
+                const int i = tid + k * (int)blockDim.x;
+                const long long row = (long long)blk * block_rows + i;
+                nx[k] = (i < block_rows && row < M) ? __ldg(x + row) : 0.0f;
+            }
+        };
+        auto store_x = [&](int buf) {
+#pragma unroll
+            for (int k = 0; k < kXPerThread; k++) {
+                const int i = tid + k * (int)blockDim.x;
+                if (i < block_rows) xbuf[buf * block_rows + i] = nx[k];
+            }
+        };
+        __syncthreads();                                  // the previous piece's chunks are retired (drain) by every warp
+        fetch_x(blk_a);
+        store_x(0);
+        __syncthreads();
+        for (int blk = blk_a; blk < blk_b; blk++) {
+            const int buf = (blk - blk_a) % 3;
+            const uint32_t g0 = g1;
+            g1 = g2;
+            if (blk + 2 <= blk_b) g2 = __ldg(ob + min(blk + 2, units));   // one block ahead
+            if (blk + 1 < blk_b) fetch_x(blk + 1);
+            int issued = 0;
+#pragma unroll 1
+            for (uint32_t g = g0 + 32u * warp; g < g1; g += 32u * n_warps) {
+                const int s = it++ & (kStages - 1);
+                cp_async_wait<kStages - 1>();
+                retire_lob(s);
+                __syncwarp();
+                cp_async16(ring_v + s * 32 + lane, vals + g + lane);
+                CI::copy(ring_i + s * 32 + lane, idx, g + lane, true);
+                cp_async_commit();
+                if (lane == 0) sinfo[s] = make_uint2(1u, (uint32_t)(buf * block_rows));
+                __syncwarp();
+                issued++;
+            }
+            // a warp that issued fewer chunks than the ring holds may still have chunks of the
+            // previous block in flight: finish them, so that only the current and the previous
+            // block's x slices are ever live when the third buffer is overwritten
+            if (issued < kStages) {
+                cp_async_wait<0>();
+#pragma unroll 1
+                for (int k = 0; k < kStages; k++) {
+                    const int s = it++ & (kStages - 1);
+                    retire_lob(s);
+                    __syncwarp();
+                    if (lane == 0) sinfo[s] = make_uint2(0u, 0u);
+                    __syncwarp();
+                }
+            }
+            if (blk + 1 < blk_b) {
+                store_x((buf + 1) % 3);
+                __syncthreads();
+            }
+        }
+    };
     int piece = 0;
     for (long long u = u_begin; u < u_end; piece++) {
-        const int slab = (int)(u / M);
-        const int row_a = (int)(u - (long long)slab * M);
-        const int row_b = (int)min((long long)M, row_a + (u_end - u));
+        const int slab = (int)(u / units);
+        const int row_a = (int)(u - (long long)slab * units);
+        const int row_b = (int)min((long long)units, row_a + (u_end - u));
         u += row_b - row_a;
 
         for (int c = lane; c < W; c += 32) acc[c] = 0.0f;
@@ -266,6 +361,9 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         // (no redundant metadata loads, one metadata latency per 256 of its rows, statistically
         // balanced).  Shorter pieces: every warp scans every block (a single batch) and keeps the
         // active rows whose rank is w modulo the warp count (exact balance).
+        if (LOB) {
+            run_blocks(slab, row_a, row_b);
+        } else {
         const int blk_a = row_a >> 5, blk_b = (row_b + 31) >> 5;
         const bool by_block = (blk_b - blk_a) >= n_warps;
         const int bstep = by_block ? n_warps : 1;
@@ -302,24 +400,27 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
                 __syncwarp();                             // the list is rewritten next
             }
         }
+        }
         SPMV_STAMP(wg, 2);
         cp_async_wait<0>();
         SPMV_STAMP(wg, 3);
 #pragma unroll 1
         for (int k = 0; k < kStages; k++) {
-            if (MR) retire_mr(it++ & (kStages - 1)); else retire(it++ & (kStages - 1));
+            if (LOB) retire_lob(it++ & (kStages - 1));
+            else if (MR) retire_mr(it++ & (kStages - 1));
+            else retire(it++ & (kStages - 1));
         }
         SPMV_STAMP(wg, 4);
 
         // ---- fixed-order sum over warps, then over the slab's pieces -----------------------------
         __syncthreads();
         SPMV_STAMP(wg, 5);
-        const long long s_begin = (long long)slab * M;
-        const long long c_lo = cta_of_unit(s_begin, T, G), c_hi = cta_of_unit(s_begin + M - 1, T, G);
+        const long long s_begin = (long long)slab * units;
+        const long long c_lo = cta_of_unit(s_begin, T, G), c_hi = cta_of_unit(s_begin + units - 1, T, G);
         const int n_pieces = (int)(c_hi - c_lo + 1);
         const int col0 = slab * W;
         const int n_valid = min(W, N - col0);
-        const int wstride = warp_smem_bytes<IDXB, kStages, MR>(W) / 4;
+        const int wstride = warp_smem_bytes<IDXB, kStages, MR, LOB>(W) / 4;
         const float *acc0 = reinterpret_cast<const float *>(smem_raw);
         float *dst = partial + ((size_t)blockIdx.x * kmax + piece) * W;
         for (int c = tid; c < n_valid; c += blockDim.x) {
@@ -336,7 +437,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
             __syncthreads();
             for (int j = tid; j < n_pieces; j += blockDim.x) {
                 const long long c = c_lo + j;
-                row_of[j] = (uint32_t)(c * kmax + (slab - (int)(range_begin(c, T, G) / M)));
+                row_of[j] = (uint32_t)(c * kmax + (slab - (int)(range_begin(c, T, G) / units)));
             }
             // (split_reduce_rows starts with a barrier, which also publishes row_of)
             split_reduce_rows(yd, (size_t)col0, [&](int j) { return partial + (size_t)row_of[j] * W; }, &tickets[slab],
@@ -347,18 +448,21 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     }
 }
 
-template <int IDXB, bool TILED, bool MR>
+template <int IDXB, bool TILED, bool MR, bool LOB = false>
 int launch_variant(spmv_plan *p, const float *x, const YDst &y, cudaStream_t st)
 {
-    auto k = panel_kernel<IDXB, TILED, MR, stages_of<MR>()>;
+    auto k = panel_kernel<IDXB, TILED, MR, stages_of<MR, LOB>(), LOB>;
     static int smem_set[16] = {0};                        // per device: largest dynamic smem opted in so far
     if (p->smem > 48 * 1024 && p->device >= 0 && p->device < 16 && smem_set[p->device] < p->smem) {
         SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem));
         smem_set[p->device] = p->smem;
     }
     const DevPanel &d = p->panel;
+    int cbits = 0;
+    while ((32 << cbits) < d.slab_cols) cbits++;
     SPMV_CUDA(launch_k(k, p->grid, dim3(p->block), p->smem, st, reinterpret_cast<const float4 *>(d.vals), d.idx, d.off, d.rel,
-                       x, y, p->partial, p->tickets, (int)p->M, (int)p->N, d.slab_cols, d.row_blocks, d.slabs, d.kmax));
+                       x, y, p->partial, p->tickets, (int)p->M, (int)p->N, d.slab_cols, d.row_blocks, d.slabs, d.kmax,
+                       LOB ? d.lob_blocks : (int)p->M, d.block_rows, cbits));
     return SPMV_OK;
 }
 
@@ -372,6 +476,7 @@ int launch_panel(spmv_plan *p, const float *d_x, const YDst &d_y, cudaStream_t s
         return SPMV_OK;
     }
     const DevPanel &d = p->panel;
+    if (d.block_rows > 0) return launch_variant<16, false, false, true>(p, d_x, d_y, st);
     if (d.multirow) {
         if (d.index_bits == 8) return d.tiled ? launch_variant<8, true, true>(p, d_x, d_y, st) : launch_variant<8, false, true>(p, d_x, d_y, st);
         return d.tiled ? launch_variant<16, true, true>(p, d_x, d_y, st) : launch_variant<16, false, true>(p, d_x, d_y, st);
@@ -390,40 +495,45 @@ int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o)
     DevPanel &d = p->panel;
     d.slab_cols = h.slab_cols; d.index_bits = h.index_bits; d.slabs = h.slabs;
     d.row_blocks = h.row_blocks; d.tiled = h.tiled;
+    d.block_rows = h.block_rows; d.lob_blocks = h.lob_blocks;
+    const bool lob = h.block_rows > 0;
     // short segments (fewer than 12 groups on average, i.e. chunks less than 3/8 full): pack
     // several rows into one chunk
     const double segs = std::max<double>(1.0, (double)h.nonempty_segments);
     d.multirow = (double)h.groups / segs < 12.0;
     if (o && o->chunk_mode == 1) d.multirow = false;
     if (o && o->chunk_mode == 2) d.multirow = true;
+    if (lob) d.multirow = false;
     const int smem_cap = p->max_smem_optin > 0 ? p->max_smem_optin : 227 * 1024;
-    const int per_warp = d.multirow ? (h.index_bits == 8 ? warp_smem_bytes<8, kMrStages, true>(h.slab_cols) : warp_smem_bytes<16, kMrStages, true>(h.slab_cols))
+    const int per_warp = lob ? warp_smem_bytes<16, kLobStages, false, true>(h.slab_cols) : d.multirow ? (h.index_bits == 8 ? warp_smem_bytes<8, kMrStages, true>(h.slab_cols) : warp_smem_bytes<16, kMrStages, true>(h.slab_cols))
                                     : (h.index_bits == 8 ? warp_smem_bytes<8, kRingStages, false>(h.slab_cols) : warp_smem_bytes<16, kRingStages, false>(h.slab_cols));
     int warps = kPanelMaxWarps;
     if (o && o->warps_per_col > 0) {
         warps = 1;
         while (warps * 2 <= std::min(kPanelMaxWarps, o->warps_per_col)) warps *= 2;   // power of two
     }
-    while (warps > 1 && warps * per_warp > smem_cap) warps /= 2;
-    if (warps * per_warp > smem_cap)
-        return set_error(SPMV_ERR_UNSUPPORTED, "panel: %d bytes of shared memory exceed the device limit", warps * per_warp);
+    const int xbuf_bytes = lob ? 3 * h.block_rows * 4 : 0;               // lane-owned blocks: three x slices per CTA
+    if (lob) warps = kPanelMaxWarps;                                      // the x slices are staged by 256 threads
+    while (!lob && warps > 1 && warps * per_warp > smem_cap) warps /= 2;
+    if (warps * per_warp + xbuf_bytes > smem_cap)
+        return set_error(SPMV_ERR_UNSUPPORTED, "panel: %d bytes of shared memory exceed the device limit", warps * per_warp + xbuf_bytes);
     d.warps = warps;
     p->block = warps * 32;
-    p->smem = warps * per_warp;
+    p->smem = warps * per_warp + xbuf_bytes;
     p->tile_width = h.slab_cols;
     p->col_tiles = h.slabs;
     p->kernels_per_run = 1;
 
     const int slabs = std::max(1, h.slabs);
-    const int64_t M = std::max<int64_t>(1, h.M);
-    const int resident = std::max(1, std::min(std::min(2, 2048 / p->block), (228 * 1024) / (p->smem + 1024)));
+    const int64_t M = std::max<int64_t>(1, lob ? h.lob_blocks : h.M);      // units per slab of the flat sequence
+    const int resident = std::max(1, std::min(std::min(lob ? 3 : 2, 2048 / p->block), (228 * 1024) / (p->smem + 1024)));
     int64_t G = (int64_t)p->sm_count * resident;
     // a whole number of CTAs per slab when that costs under 10 % of the grid: no piece crosses a
     // slab boundary, so no CTA pays the per-piece overhead twice (288 vs 296 CTAs: 11.9 vs 13.8 us)
     if (G >= slabs && (G / slabs) * slabs * 10 >= G * 9) G = (G / slabs) * slabs;
     if (o && o->row_splits > 0) G = (int64_t)slabs * o->row_splits;       // forced: row_splits CTAs per slab
     const int64_t T = (int64_t)slabs * M;
-    G = std::max<int64_t>(1, std::min<int64_t>(G, (T + 31) / 32));         // at least 32 rows per CTA
+    G = std::max<int64_t>(1, std::min<int64_t>(G, lob ? T : (T + 31) / 32));   // at least 32 rows (one block) per CTA
     const int64_t max_range = (T + G - 1) / G;
     d.kmax = (int)(2 + max_range / M);
     p->row_splits = (int)((G + slabs - 1) / slabs);                        // reported: CTAs per slab (rounded up)

@@ -50,9 +50,9 @@ int pack_wsp_dense(int64_t M, int64_t N, const float *A, int64_t lda, int index_
 int pack_wsp_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx,
                  const float *values, int index_bits, HostWsp &w);
 int pack_panel_dense(int64_t M, int64_t N, const float *A, int64_t lda, bool tiled, int slab_cols,
-                     HostPanel &P);
+                     HostPanel &P, bool lane_owned = false);
 int pack_panel_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx,
-                   const float *values, bool tiled, int slab_cols, HostPanel &P);
+                   const float *values, bool tiled, int slab_cols, HostPanel &P, bool lane_owned = false);
 int choose_slab_cols(int64_t M, int64_t N, int64_t nnz);
 void wsp_choose_panels(HostWsp &w, int64_t nnz, int index_bits_opt);   // sets panels, panel_rows, index_bits
 
@@ -86,6 +86,8 @@ struct DevPanel {
     int kmax = 2;               // partial rows reserved per CTA (pieces of its flat range)
     bool tiled = false;
     bool multirow = false;      // several short rows per 32-group chunk
+    int block_rows = 0;         // > 0: lane-owned blocks (formats.hpp), off is per (slab, block)
+    int lob_blocks = 0;
 };
 
 } // namespace spmv

@@ -246,7 +246,7 @@ def pack_dump(variant, A=None, csc=None, shape=None, **opts):
     if d.idx and nidx:
         idx = np.frombuffer(C.string_at(d.idx, d.idx_bytes), dtype=idt).copy()
     out = SimpleNamespace(variant=variant, index_bits=d.index_bits, slab_cols=d.slab_cols, slabs=d.slabs,
-                          row_blocks=d.row_blocks, M=d.M, N=d.N, nnz=d.nnz, groups=d.groups,
+                          row_blocks=d.row_blocks, block_rows=d.block_rows, M=d.M, N=d.N, nnz=d.nnz, groups=d.groups,
                           vals=arr(d.vals, d.n_vals, np.float32), idx=idx,
                           off=arr(d.off, d.n_off, np.uint32), rel=arr(d.rel, d.n_rel, np.uint16))
     lib().spmv_pack_dump_free(C.byref(d))

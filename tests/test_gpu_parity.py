@@ -490,3 +490,52 @@ def test_device_packers_options_and_views(S, tmp_path):
         check(lib().spmv_plan_create_dense_device(V["awsp"], 1024, 2048, C.c_void_p(A.ctypes.data), 2048, None, C.byref(h)))
     with pytest.raises(S.SpmvError):
         S.Plan.from_dense("awsp", A, pack_mode=7)
+
+
+# ---- lane-owned blocks (chunk_mode 3) --------------------------------------------------------------
+LOB_SHAPES = [
+    # M, N, weight sparsity, activation sparsity, slab_cols (0 = default 2048)
+    (32, 32, 0.5, 0.5, 0), (1, 64, 0.0, 0.0, 1024), (1000, 512, 0.7, 0.5, 1024), (2049, 2048 + 96, 0.98, 0.5, 0),
+    (5000, 4096, 0.99, 0.5, 1024), (3000, 8192, 0.995, 0.0, 4096), (70000, 512, 0.99, 0.9, 0), (4096, 4096, 0.5, 0.5, 1024),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,sa,sx,W", LOB_SHAPES)
+def test_lane_owned_blocks_parity(S, M, N, sa, sx, W, tmp_path):
+    """chunk_mode 3: x is a multiplier, every chunk retires in one pass; same parity bar, and the
+    CSR(A^T) route, a saved plan and a clone give the same bits."""
+    A = ob.gen_matrix(M, N, sa, 1234)
+    if M > 40:
+        A[:, 3] = 0.25                                                   # one long lane stream
+        A[37, :] = 0.0
+    x = ob.gen_vector(M, sx, 4321)
+    kw = {"slab_cols": W} if W else {}
+    ys = run_all(S, A, x, variants=("awsp", "tcsr"), chunk_mode=3, **kw)
+    assert ys["awsp"].tobytes() == ys["tcsr"].tobytes()
+    from scipy import sparse
+    c = sparse.csc_matrix(A)
+    with S.Plan.from_csc("awsp", M, N, c.indptr.astype(np.int64), c.indices.astype(np.int32), c.data.astype(np.float32),
+                         chunk_mode=3, **kw) as p:
+        assert p.run_host(x).tobytes() == ys["awsp"].tobytes()
+        p.save(tmp_path / "lob.plan")
+        with p.clone() as q:
+            assert q.run_host(x).tobytes() == ys["awsp"].tobytes()
+        alg, phys, touched = p.traffic(x)
+        assert touched == int(np.count_nonzero(A[x != 0.0])) and phys > 0
+    with S.Plan.load(tmp_path / "lob.plan") as q:
+        assert q.run_host(x).tobytes() == ys["awsp"].tobytes()
+    raw = bytearray((tmp_path / "lob.plan").read_bytes())
+    if len(raw) > 4000:
+        raw[len(raw) // 2] ^= 0xFF
+        (tmp_path / "bad.plan").write_bytes(bytes(raw[:-9]))
+        with pytest.raises(S.SpmvError):
+            S.Plan.load(tmp_path / "bad.plan")
+
+
+@pytest.mark.gpu
+def test_lane_owned_blocks_many_ctas_per_slab_and_forced_splits(S):
+    A = ob.gen_matrix(40000, 2048, 0.99, 77)
+    x = ob.gen_vector(40000, 0.5, 78)
+    for o in (dict(), dict(row_splits=1), dict(row_splits=7), dict(warps_per_col=2)):
+        run_all(S, A, x, variants=("awsp",), chunk_mode=3, **o)

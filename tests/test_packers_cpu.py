@@ -154,3 +154,57 @@ def test_wsp_row_panels_for_tall_matrices():
     assert d.vals.tobytes() == e.vals.tobytes() and d.idx.tobytes() == e.idx.tobytes() and d.off.tobytes() == e.off.tobytes()
     thin = S.pack_dump("wsp", ob.gen_matrix(40000, 64, 0.9995, 18))      # lists too short: one panel, x through L2
     assert thin.slabs == 1 and thin.slab_cols == 40000
+
+
+# ---- lane-owned blocks (chunk_mode 3) ---------------------------------------------------------------
+def _decode_lane_owned(d):
+    """Dense matrix from the lane-owned block format (formats.hpp), checking its invariants."""
+    W, R = d.slab_cols, d.block_rows
+    cbits = (W // 32).bit_length() - 1
+    assert R == min(1024, 1 << (16 - cbits)) and d.index_bits == 16 and d.groups % 32 == 0
+    nb = (d.M + R - 1) // R
+    A = np.zeros((d.M, d.N), np.float32)
+    seen = np.zeros((d.M, d.N), bool)
+    off = d.off.reshape(d.slabs, nb + 1)
+    vals = d.vals.reshape(-1, 4)
+    idx = d.idx.reshape(-1, 4)
+    for s in range(d.slabs):
+        for b in range(nb):
+            g0, g1 = int(off[s, b]), int(off[s, b + 1])
+            assert g0 % 32 == 0 and g1 % 32 == 0 and g0 <= g1
+            for g in range(g0, g1):
+                lane = (g - g0) % 32
+                for e in range(4):
+                    v, i = vals[g, e], int(idx[g, e])
+                    row, col = b * R + (i >> cbits), s * W + (i & ((1 << cbits) - 1)) * 32 + lane
+                    assert row < d.M                                   # pads too: x[row] must exist
+                    if v != 0.0 or np.isnan(v):
+                        assert col < d.N and not seen[row, col]
+                        seen[row, col] = True
+                        A[row, col] = v
+            if b + 1 < nb:
+                assert off[s, b + 1] >= off[s, b]
+        if s + 1 < d.slabs:
+            assert off[s + 1, 0] == off[s, nb]
+    return A
+
+
+@pytest.mark.parametrize("shape,keep,W", [((100, 256), 0.3, 1024), ((1500, 4096), 0.02, 0), ((2100, 2048 + 64), 0.01, 2048),
+                                          ((64, 1024), 1.0, 1024), ((40, 512), 0.0, 4096)])
+def test_lane_owned_blocks_hold_the_matrix(shape, keep, W):
+    import spmv_test_b200 as S
+    rng = np.random.default_rng(shape[0] + shape[1])
+    A = rng.uniform(-1, 1, shape).astype(np.float32)
+    A[rng.random(shape) >= keep] = 0.0
+    if keep > 0:
+        A[:, 7] = 1.5                                                   # a dense column: one lane's stream is much longer
+    kw = {"slab_cols": W} if W else {}
+    d = S.pack_dump("awsp", A, chunk_mode=3, **kw)
+    assert d.block_rows == min(1024, (65536 * 32) // d.slab_cols) and d.slab_cols == (W or 2048)
+    assert d.nnz == np.count_nonzero(A)
+    assert np.array_equal(_decode_lane_owned(d), A)
+    # the CSR(A^T) source builds the same bytes
+    from scipy import sparse
+    c = sparse.csc_matrix(A)
+    d2 = S.pack_dump("awsp", csc=(c.indptr, c.indices, c.data), shape=shape, chunk_mode=3, **kw)
+    assert d2.vals.tobytes() == d.vals.tobytes() and d2.idx.tobytes() == d.idx.tobytes() and d2.off.tobytes() == d.off.tobytes()
