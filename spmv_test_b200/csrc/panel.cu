@@ -259,13 +259,11 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     // the current block streams).  All warps of the CTA walk the same blocks, each taking every
     // n_warps-th chunk.
     float *xbuf = reinterpret_cast<float *>(smem_raw + (size_t)n_warps * warp_smem_bytes<IDXB, kStages, MR, LOB>(W));
-    auto retire_lob = [&](int s) {
-        const uint2 info = sinfo[s];                      // (live, x buffer of the block)
-        if (!info.x) return;
+    auto retire_lob = [&](int s, uint32_t xo) {           // xo: where the chunk's block keeps its x slice
         const float4 a = ring_v[s * 32 + lane];
         uint32_t c[4];
         CI::unpack(ring_i[s * 32 + lane], c);
-        const float *xb = xbuf + info.y;
+        const float *xb = xbuf + xo;
         const uint32_t cmask = (1u << cbits) - 1u;
         const float p0 = xb[c[0] >> cbits], p1 = xb[c[1] >> cbits], p2 = xb[c[2] >> cbits], p3 = xb[c[3] >> cbits];
         float *al = acc + lane;
@@ -276,6 +274,10 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         { float *q = al + ((c[3] & cmask) << 5); *q = fmaf(a.w, p3, *q); }
     };
     constexpr int kXPerThread = kLobMaxBlockRows / kPanelThreads;   // block_rows <= 1024, 256 threads
+    // The ring slots are visited in a fixed rotation (the loop body is unrolled over them), so what a
+    // slot holds — nothing, or a chunk and the x slice that goes with it — lives in registers: no
+    // slot table in shared memory, no warp-level synchronisation at all (a lane reads back only what
+    // it copied itself and only touches its own accumulators).
     auto run_blocks = [&](int slab, int blk_a, int blk_b) {
         const uint32_t *ob = off + (size_t)slab * (units + 1);
         uint32_t g1 = __ldg(ob + blk_a), g2 = __ldg(ob + blk_a + 1);
@@ -295,42 +297,41 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
                 if (i < block_rows) xbuf[buf * block_rows + i] = nx[k];
             }
         };
-        __syncthreads();                                  // the previous piece's chunks are retired (drain) by every warp
+        bool live[kStages]; uint32_t xo[kStages];
+#pragma unroll
+        for (int s = 0; s < kStages; s++) { live[s] = false; xo[s] = 0u; }
+        __syncthreads();                                  // every warp has left the previous piece
         fetch_x(blk_a);
         store_x(0);
         __syncthreads();
+        const uint32_t stride = 32u * n_warps;
         for (int blk = blk_a; blk < blk_b; blk++) {
             const int buf = (blk - blk_a) % 3;
+            const uint32_t xoff = (uint32_t)(buf * block_rows);
             const uint32_t g0 = g1;
             g1 = g2;
             if (blk + 2 <= blk_b) g2 = __ldg(ob + min(blk + 2, units));   // one block ahead
             if (blk + 1 < blk_b) fetch_x(blk + 1);
-            int issued = 0;
-#pragma unroll 1
-            for (uint32_t g = g0 + 32u * warp; g < g1; g += 32u * n_warps) {
-                const int s = it++ & (kStages - 1);
-                cp_async_wait<kStages - 1>();
-                retire_lob(s);
-                __syncwarp();
-                cp_async16(ring_v + s * 32 + lane, vals + g + lane);
-                CI::copy(ring_i + s * 32 + lane, idx, g + lane, true);
-                cp_async_commit();
-                if (lane == 0) sinfo[s] = make_uint2(1u, (uint32_t)(buf * block_rows));
-                __syncwarp();
-                issued++;
-            }
-            // a warp that issued fewer chunks than the ring holds may still have chunks of the
-            // previous block in flight: finish them, so that only the current and the previous
-            // block's x slices are ever live when the third buffer is overwritten
-            if (issued < kStages) {
-                cp_async_wait<0>();
-#pragma unroll 1
-                for (int k = 0; k < kStages; k++) {
-                    const int s = it++ & (kStages - 1);
-                    retire_lob(s);
-                    __syncwarp();
-                    if (lane == 0) sinfo[s] = make_uint2(0u, 0u);
-                    __syncwarp();
+            // One turn of the rotation retires everything issued before it, so at the end of a
+            // block only this block's chunks are in flight — a turn is made even when the warp
+            // has no chunk here — and only the current and the previous block's x slices are
+            // ever live when the third buffer is overwritten.
+            uint32_t g = g0 + 32u * warp;
+            bool first = true;
+            while (first || g < g1) {
+                first = false;
+#pragma unroll
+                for (int s = 0; s < kStages; s++) {
+                    cp_async_wait<kStages - 1>();
+                    if (live[s]) retire_lob(s, xo[s]);
+                    const bool have = g < g1;
+                    if (have) {
+                        cp_async16(ring_v + s * 32 + lane, vals + g + lane);
+                        CI::copy(ring_i + s * 32 + lane, idx, g + lane, true);
+                        g += stride;
+                    }
+                    cp_async_commit();
+                    live[s] = have; xo[s] = xoff;
                 }
             }
             if (blk + 1 < blk_b) {
@@ -338,6 +339,10 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
                 __syncthreads();
             }
         }
+        cp_async_wait<0>();
+#pragma unroll
+        for (int s = 0; s < kStages; s++)
+            if (live[s]) retire_lob(s, xo[s]);
     };
     int piece = 0;
     for (long long u = u_begin; u < u_end; piece++) {
@@ -405,10 +410,8 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         cp_async_wait<0>();
         SPMV_STAMP(wg, 3);
 #pragma unroll 1
-        for (int k = 0; k < kStages; k++) {
-            if (LOB) retire_lob(it++ & (kStages - 1));
-            else if (MR) retire_mr(it++ & (kStages - 1));
-            else retire(it++ & (kStages - 1));
+        for (int k = 0; k < kStages && !LOB; k++) {       // (run_blocks drains its own ring)
+            if (MR) retire_mr(it++ & (kStages - 1)); else retire(it++ & (kStages - 1));
         }
         SPMV_STAMP(wg, 4);
 
