@@ -148,13 +148,13 @@ int exclusive_scan_u32(const uint32_t *in, uint32_t *out, size_t n, unsigned lon
 __global__ void __launch_bounds__(256) count_nnz_kernel(const float *__restrict__ A, long long lda, int M, int N,
                                                         unsigned long long *__restrict__ total)
 {
-    unsigned n = 0;
+    __shared__ unsigned long long ws[8];
+    unsigned long long n = 0;
     for (int r = blockIdx.y; r < M; r += gridDim.y)
         for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x)
             n += A[(long long)r * lda + c] != 0.0f;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(kFull, n, d);
-    if ((threadIdx.x & 31) == 0 && n) atomicAdd(total, (unsigned long long)n);
+    n = block_sum_u64(n, ws);
+    if (threadIdx.x == 0 && n) atomicAdd(total, n);     // one atomic per CTA
 }
 
 int count_nnz(const float *d_A, int64_t lda, int64_t M, int64_t N, int64_t *nnz)
@@ -164,7 +164,7 @@ int count_nnz(const float *d_A, int64_t lda, int64_t M, int64_t N, int64_t *nnz)
     int rc = tmp.get(&total, 1, true);
     if (rc) return rc;
     if (M > 0 && N > 0) {
-        dim3 grid((unsigned)std::min<int64_t>((N + 255) / 256, 64), (unsigned)std::min<int64_t>(M, 4096));
+        dim3 grid((unsigned)std::min<int64_t>((N + 255) / 256, 16), (unsigned)std::min<int64_t>(M, 296));
         count_nnz_kernel<<<grid, 256>>>(d_A, lda, (int)M, (int)N, total);
         SPMV_CUDA(cudaGetLastError());
     }
