@@ -288,6 +288,7 @@ void pack_slab_lob(int s, int64_t M, int W, int R, Source &src, SlabOut &O, RowS
     O.off.assign((size_t)NB + 1, 0);
     std::vector<uint16_t> cols((size_t)W + 4), li[32];
     std::vector<float> vals((size_t)W + 4), lv[32];
+    std::vector<int64_t> lp[32];                           // position of every entry inside its lane's stream
     src.begin_slab(s);
     for (int64_t b = 0; b < NB; b++) {
         O.off[(size_t)b] = (uint32_t)O.groups;
@@ -304,21 +305,41 @@ void pack_slab_lob(int s, int64_t M, int W, int R, Source &src, SlabOut &O, RowS
         }
         size_t longest = 0;
         for (int l = 0; l < 32; l++) longest = std::max(longest, li[l].size());
-        const int64_t G = (int64_t)((longest + 3) / 4);    // chunks of this block
+        // Row-aligned streams: an entry of row r is never placed before chunk floor(r * G0 / span) - slack,
+        // so a lane with few entries gets its pads in between rather than at the end and all 32
+        // lanes of a chunk look at rows a few apart — their x look-ups (x slice in shared memory,
+        // bank = row mod 32) then fall into distinct banks.
+        const int64_t G0 = (int64_t)((longest + 3) / 4);
+        const int64_t span = r1 - b * R;
+        constexpr int64_t slack = 6;   // chunks an entry may run ahead of its row: 8.9 % padding and 1.8 wavefronts per
+                                       // look-up on config 5 (0: 12.2 % / 1.4; unaligned streams: 8.5 % / 2.4)
+        int64_t G = G0;
+        for (int l = 0; l < 32; l++) {
+            lp[l].resize(li[l].size());
+            int64_t prev = -1;
+            for (size_t k = 0; k < li[l].size(); k++) {
+                const int64_t row = li[l][k] >> cbits;
+                prev = std::max(prev + 1, 4 * std::max<int64_t>(0, row * G0 / span - slack));
+                lp[l][k] = prev;
+            }
+            if (prev >= 0) G = std::max(G, prev / 4 + 1);
+        }
         const size_t at = O.vals.size();
         O.vals.resize(at + (size_t)G * 128);
         O.idx16.resize(at + (size_t)G * 128);
-        for (int64_t g = 0; g < G; g++)
-            for (int l = 0; l < 32; l++) {
-                // a pad repeats the lane's last entry with value 0: same accumulator, a row that exists
-                const uint16_t pad = li[l].empty() ? (uint16_t)0 : li[l].back();
-                for (int e = 0; e < 4; e++) {
-                    const size_t k = (size_t)g * 4 + e, o = at + ((size_t)g * 32 + l) * 4 + e;
-                    const bool real = k < li[l].size();
-                    O.vals[o] = real ? lv[l][k] : 0.0f;
-                    O.idx16[o] = real ? li[l][k] : pad;
+        for (int l = 0; l < 32; l++) {
+            // a pad repeats the next real entry of the lane (the last one after the end) with
+            // value 0: same accumulator, a row that exists and lies in the chunk's row window
+            size_t k = 0;
+            for (int64_t pos = 0; pos < 4 * G; pos++) {
+                const size_t o = at + ((size_t)(pos >> 2) * 32 + l) * 4 + (pos & 3);
+                if (k < li[l].size() && lp[l][k] == pos) { O.vals[o] = lv[l][k]; O.idx16[o] = li[l][k]; k++; }
+                else {
+                    O.vals[o] = 0.0f;
+                    O.idx16[o] = li[l].empty() ? (uint16_t)0 : li[l][std::min(k, li[l].size() - 1)];
                 }
             }
+        }
         O.groups += G * 32;
         if (O.groups >= (int64_t)UINT32_MAX) { O.rc = SPMV_ERR_UNSUPPORTED; return; }
     }
