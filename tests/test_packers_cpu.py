@@ -208,3 +208,11 @@ def test_lane_owned_blocks_hold_the_matrix(shape, keep, W):
     c = sparse.csc_matrix(A)
     d2 = S.pack_dump("awsp", csc=(c.indptr, c.indices, c.data), shape=shape, chunk_mode=3, **kw)
     assert d2.vals.tobytes() == d.vals.tobytes() and d2.idx.tobytes() == d.idx.tobytes() and d2.off.tobytes() == d.off.tobytes()
+
+
+def test_lane_owned_blocks_reject_narrow_slabs():
+    import spmv_test_b200 as S
+    A = ob.gen_matrix(64, 512, 0.5, 3)
+    for w in (256, 512):
+        with pytest.raises(S.SpmvError):
+            S.pack_dump("awsp", A, chunk_mode=3, slab_cols=w)
