@@ -184,6 +184,16 @@ SPMV_API int spmv_plan_traffic(const spmv_plan_t *plan, const float *x, double *
 SPMV_API int spmv_run(spmv_plan_t *plan, const float *d_x, float *d_y, void *stream);
 
 /*
+ * The same with an activation fused into the stores of y: y = act(x·A).  In a decode FFN
+ * (BASELINE configs 2 -> 3: up-projection, activation, down-projection) the intermediate then
+ * leaves the first kernel already rectified, and the second call's fused `x != 0` compaction skips
+ * its zeros: two launches, no elementwise kernel, no compaction pass in between.
+ * ReLU is `v < 0 ? 0 : v` (NaN is kept).
+ */
+typedef enum spmv_activation { SPMV_ACT_NONE = 0, SPMV_ACT_RELU = 1 } spmv_activation_t;
+SPMV_API int spmv_run_act(spmv_plan_t *plan, const float *d_x, float *d_y, int activation, void *stream);
+
+/*
  * Batched (multi-vector) form, SURVEY section 8f-2: Y[b] = X[b] * A for b < batch, X row-major
  * batch x M (row stride ldx), Y row-major batch x N (row stride ldy, multiple of 4), device
  * pointers.  wsp plans stream A once per group of 4 (or 2) vectors with all of them in shared

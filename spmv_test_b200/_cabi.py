@@ -15,7 +15,7 @@ LAYOUTS = {"csr": 0, "tcsr": 1, "wsp": 2, "asp": 3, "awsp": 4, "awsp_ref": 5}
 SYMBOLS = [
     "spmv_abi_version", "spmv_last_error", "spmv_device_count", "spmv_plan_create_dense", "spmv_plan_create_dense_device",
     "spmv_plan_create_csc", "spmv_plan_info", "spmv_plan_destroy", "spmv_plan_clone", "spmv_plan_save", "spmv_plan_load",
-    "spmv_plan_traffic", "spmv_run", "spmv_run_batch", "spmv_run_scatter", "spmv_run_host", "spmv_compact_x",
+    "spmv_plan_traffic", "spmv_run", "spmv_run_act", "spmv_run_batch", "spmv_run_scatter", "spmv_run_host", "spmv_compact_x",
     "spmv_compact_x_scratch_bytes", "spmv_partition_columns", "spmv_ref_pack",
     "spmv_ref_packed_free", "spmv_pack_dump_dense", "spmv_pack_dump_csc", "spmv_pack_dump_free",
 ]
@@ -87,6 +87,7 @@ def lib():
     L.spmv_plan_load.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(vp)]
     L.spmv_plan_traffic.argtypes = [vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
     L.spmv_run.argtypes = [vp, vp, vp, vp]
+    L.spmv_run_act.argtypes = [vp, vp, vp, i32, vp]
     L.spmv_run_batch.argtypes = [vp, i32, vp, i64, vp, i64, vp]
     L.spmv_run_scatter.argtypes = [vp, vp, i32, C.POINTER(vp), vp, i64, vp]
     L.spmv_run_host.argtypes = [vp, vp, vp, C.POINTER(C.c_float)]

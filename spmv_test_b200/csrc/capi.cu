@@ -672,14 +672,24 @@ static int run_to(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t s
     return set_error(SPMV_ERR_ARG, "corrupt plan");
 }
 
-int spmv_run(spmv_plan_t *p, const float *d_x, float *d_y, void *stream)
+int spmv_run_act(spmv_plan_t *p, const float *d_x, float *d_y, int activation, void *stream)
 {
     if (!p) return set_error(SPMV_ERR_ARG, "null plan");
     if ((!d_x && p->M > 0) || (!d_y && p->N > 0)) return set_error(SPMV_ERR_ARG, "null device vector");
     if ((reinterpret_cast<uintptr_t>(d_y) & 15) != 0) return set_error(SPMV_ERR_ARG, "d_y must be 16-byte aligned");
+    if (activation != SPMV_ACT_NONE && activation != SPMV_ACT_RELU) return set_error(SPMV_ERR_ARG, "unknown activation %d", activation);
+    if (activation != SPMV_ACT_NONE && p->M == 0 && p->N > 0) {      // y = act(0) = 0
+        SPMV_CUDA(cudaMemsetAsync(d_y, 0, (size_t)p->N * sizeof(float), reinterpret_cast<cudaStream_t>(stream)));
+        return SPMV_OK;
+    }
     YDst yd{};
-    yd.p[0] = d_y; yd.n = 1; yd.mc = nullptr;
+    yd.p[0] = d_y; yd.n = 1; yd.mc = nullptr; yd.act = activation;
     return run_to(p, d_x, yd, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int spmv_run(spmv_plan_t *p, const float *d_x, float *d_y, void *stream)
+{
+    return spmv_run_act(p, d_x, d_y, SPMV_ACT_NONE, stream);
 }
 
 int spmv_run_batch(spmv_plan_t *p, int batch, const float *d_X, int64_t ldx, float *d_Y, int64_t ldy, void *stream)

@@ -43,9 +43,13 @@ struct YDst {
     float *p[kMaxYDst];      // base pointers, already offset to this rank's slice
     float *mc;               // multicast alias of the same slice (or null)
     int n;
+    int act;                 // activation fused into the store: 0 none, 1 ReLU (spmv_run_act)
 };
+// ReLU as `v < 0 ? 0 : v`: NaN stays NaN; the next SGEMV's `x != 0` test then skips the zeros
+__device__ __forceinline__ float y_act(const YDst &d, float v) { return (d.act == 1 && v < 0.0f) ? 0.0f : v; }
 __device__ __forceinline__ void y_store(const YDst &d, size_t i, float v)
 {
+    v = y_act(d, v);
     if (d.mc) {
         asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(d.mc + i), "r"(__float_as_uint(v)) : "memory");
     } else {
@@ -55,6 +59,7 @@ __device__ __forceinline__ void y_store(const YDst &d, size_t i, float v)
 }
 __device__ __forceinline__ void y_store4(const YDst &d, size_t i4, float4 v)   // i4: index in float4 units
 {
+    v.x = y_act(d, v.x); v.y = y_act(d, v.y); v.z = y_act(d, v.z); v.w = y_act(d, v.w);
     if (d.mc) {
         unsigned long long lo, hi;
         asm("mov.b64 %0, {%1, %2};" : "=l"(lo) : "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)));

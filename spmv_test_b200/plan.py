@@ -134,14 +134,19 @@ class Plan:
         return a.value, p.value, n.value
 
     # ---- execution -------------------------------------------------------------------------
-    def run(self, d_x, d_y, stream=None):
-        """Asynchronous y = x·A on device tensors (torch CUDA tensors or raw pointers)."""
+    def run(self, d_x, d_y, stream=None, act=None):
+        """Asynchronous y = x·A on device tensors (torch CUDA tensors or raw pointers);
+        act="relu" fuses the activation into the stores of y (spmv_run_act)."""
         px = d_x if isinstance(d_x, int) else d_x.data_ptr()
         py = d_y if isinstance(d_y, int) else d_y.data_ptr()
         if stream is None:
             import torch
             stream = torch.cuda.current_stream().cuda_stream
-        check(lib().spmv_run(self._h, C.c_void_p(px), C.c_void_p(py), C.c_void_p(stream)))
+        if act is None:
+            check(lib().spmv_run(self._h, C.c_void_p(px), C.c_void_p(py), C.c_void_p(stream)))
+        else:
+            code = {"none": 0, "relu": 1}[act] if isinstance(act, str) else int(act)
+            check(lib().spmv_run_act(self._h, C.c_void_p(px), C.c_void_p(py), code, C.c_void_p(stream)))
 
     def run_batch(self, d_X, d_Y, stream=None):
         """Y[b] = X[b]·A for a batch of activation vectors (2-D CUDA tensors, row-major)."""

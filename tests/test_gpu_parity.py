@@ -539,3 +539,38 @@ def test_lane_owned_blocks_many_ctas_per_slab_and_forced_splits(S):
     x = ob.gen_vector(40000, 0.5, 78)
     for o in (dict(), dict(row_splits=1), dict(row_splits=7), dict(warps_per_col=2)):
         run_all(S, A, x, variants=("awsp",), chunk_mode=3, **o)
+
+
+# ---- fused activation and the decode FFN chain ---------------------------------------
+@pytest.mark.gpu
+def test_fused_relu_and_ffn_chain(S):
+    """y = relu(x·A) through the store epilogue is bit-identical to a separate ReLU, for every
+    variant; the up-projection -> ReLU -> down-projection chain (configs 2 -> 3, scaled) runs as two
+    launches and matches the oracle."""
+    import torch
+    M, H = 512, 2048
+    A1 = ob.gen_matrix(M, H, 0.7, 11)
+    A2 = ob.gen_matrix(H, M, 0.7, 12)
+    x = ob.gen_vector(M, 0.5, 13)
+    dx = torch.from_numpy(x).cuda()
+    for v in VARIANTS + ["awsp3"]:
+        kw = {"chunk_mode": 3} if v == "awsp3" else {}
+        with S.Plan.from_dense(v[:4] if v == "awsp3" else v, A1, **kw) as p:
+            y = torch.empty(H, device="cuda"); yr = torch.empty(H, device="cuda")
+            p.run(dx, y); p.run(dx, yr, act="relu")
+            torch.cuda.synchronize()
+            yn = y.cpu().numpy()
+            assert np.array_equal(yr.cpu().numpy(), np.where(yn < 0, np.float32(0), yn)), v
+            assert np.any(yn < 0)
+    with S.Plan.from_dense("wsp", A1) as up, S.Plan.from_dense("awsp", A2) as down:
+        h = torch.empty(H, device="cuda"); z = torch.empty(M, device="cuda")
+        up.run(dx, h, act="relu")
+        down.run(h, z)                                                  # its prologue compacts the rectified h
+        torch.cuda.synchronize()
+        hn = h.cpu().numpy()
+        assert 0.3 < float(np.mean(hn == 0)) < 0.7                      # about half of the intermediate is inactive
+        y32, y64, s = refs(A2, hn)
+        check_y(z.cpu().numpy(), y32, y64, s, "ffn chain")
+    with pytest.raises(S.SpmvError):
+        with S.Plan.from_dense("asp", A1) as p:
+            p.run(dx, torch.empty(H, device="cuda"), act=7)
