@@ -181,9 +181,11 @@ int launch_asp_batch(spmv_plan *p, const float *d_x, long long ldx, const YDst &
     return SPMV_ERR_UNSUPPORTED;
 }
 
-// grid = (ceil(N/512), row splits): a little over two CTAs per SM, all resident at once — every
-// CTA pays a fixed few microseconds (x compaction, first rows, split reduction), so more splits
-// are slower (measured: 8-12 splits 24.7 us, 16 splits 26.9 us on config 2) — at least 64 rows each.
+// grid = (ceil(N/512), row splits): about 1.6 CTAs per SM, all resident at once — every CTA pays a
+// fixed few microseconds (x compaction, first rows, split reduction), so more splits are slower —
+// with the rows per split rounded DOWN to a multiple of 32 (at least 64).  Measured with dependent
+// launch on (profiles/r01_notes.md): config 2 8 splits 23.8 us, 12 splits 24.3, 16 splits 26.9;
+// config 3 32 splits 9.4 us, 41 splits 10.3; config 0 32 splits 11.7 us, 16 splits 12.2.
 int configure_asp(spmv_plan *p, const spmv_options_t *o)
 {
     p->block = kAspThreads;
@@ -195,10 +197,10 @@ int configure_asp(spmv_plan *p, const spmv_options_t *o)
     const int64_t M = std::max<int64_t>(p->M, 1);
     int splits;
     if (o && o->row_splits > 0) splits = (int)std::min<int64_t>(o->row_splits, M);
-    else splits = std::max(1, (9 * p->sm_count / 4 + p->col_tiles / 2) / std::max(1, p->col_tiles));
-    int rps = (int)((M + splits - 1) / splits);
-    if (!(o && o->row_splits > 0)) rps = std::max(64, rps);
-    rps = (rps + 31) / 32 * 32;
+    else splits = std::max(1, (16 * p->sm_count / 10 + p->col_tiles / 2) / std::max(1, p->col_tiles));
+    int rps;
+    if ((o && o->row_splits > 0) || splits == 1) rps = ((int)((M + splits - 1) / splits) + 31) / 32 * 32;
+    else rps = std::max(64, (int)(M / splits) / 32 * 32);
     splits = (int)((M + rps - 1) / rps);
     p->asp.rows_per_split = rps;
     p->row_splits = splits;
