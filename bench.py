@@ -10,9 +10,10 @@ N = 1   workload = BASELINE config 2 (LLM decode FFN up-proj: A 4096x14336, 70 %
         single-GPU configs) is also timed alone and reported under "variants" / "configs", and
         "roofline" describes the step's dominant (longest) kernel.
 N > 1   workload = BASELINE config 5 family, weak scaling: every rank owns a 131072-column slab
-        of A (65536 rows, 99 % sparse, built directly in sparse form), x is replicated, a step is
-        the local awsp call plus the NCCL all-gather of Y.  At N = 8 this is exactly config 5
-        (65536 x 1048576).  The N = 1 line also carries this slab's single-GPU number
+        of A (65536 rows, 99 % sparse, built directly in sparse form; lane-owned block form of the
+        awsp format, chunk_mode 3), x is replicated, a step is the local awsp call whose epilogue
+        stores its slice of Y into every rank's buffer (fused all-gather; the NCCL all-gather join
+        is timed beside it, "join").  At N = 8 this is exactly config 5 (65536 x 1048576).  The N = 1 line also carries this slab's single-GPU number
         ("weak_scaling_unit") so per-N efficiency can be computed on one workload.
 
 value   = algorithmic bytes (8*nnz_touched + 4(N+1) + 4M + 4N) of all ranks divided by
