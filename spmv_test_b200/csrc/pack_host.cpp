@@ -40,24 +40,48 @@ static void wsp_finish_layout(HostWsp &w, const std::vector<int64_t> &list_nnz)
     else w.idx32.assign((size_t)(g + 1) * 4, pad);
 }
 
-// In-chunk order for the kernel's shared-memory gathers of x (deal.hpp).
+static int pack_threads(int64_t work_items)
+{
+    int n = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    if (const char *e = std::getenv("SPMV_PACK_THREADS")) n = std::max(1, std::atoi(e));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(n, work_items));
+}
+
+// In-chunk order for the kernel's shared-memory gathers of x (deal.hpp).  Lists are independent:
+// a small pool of host threads takes contiguous ranges of them (same bytes for any thread count).
 template <class IdxT> static void wsp_bank_deal(HostWsp &w, std::vector<IdxT> &idx)
 {
-    IdxT oi[128], li[128];
-    float ov[128], lv[128];
     const int64_t L = (int64_t)w.panels * w.N;
-    for (int64_t c = 0; c < L; c++)
-        for (int64_t c0 = w.colptr[c]; c0 < w.colptr[c + 1]; c0 += 32) {
-            const int lanes = (int)std::min<int64_t>(32, w.colptr[c + 1] - c0);
-            const size_t first = (size_t)c0 * 4;
-            const int count = 4 * lanes;
-            std::copy(idx.begin() + first, idx.begin() + first + count, li);
-            std::copy(w.vals.begin() + first, w.vals.begin() + first + count, lv);
-            deal_chunk(lanes, [&](int k) { return (unsigned)li[k]; },
-                       [&](int slot, int k) { oi[slot] = li[k]; ov[slot] = lv[k]; });
-            std::copy(oi, oi + count, idx.begin() + first);
-            std::copy(ov, ov + count, w.vals.begin() + first);
-        }
+    auto deal_lists = [&](int64_t l0, int64_t l1) {
+        IdxT oi[128], li[128];
+        float ov[128], lv[128];
+        for (int64_t c = l0; c < l1; c++)
+            for (int64_t c0 = w.colptr[c]; c0 < w.colptr[c + 1]; c0 += 32) {
+                const int lanes = (int)std::min<int64_t>(32, w.colptr[c + 1] - c0);
+                const size_t first = (size_t)c0 * 4;
+                const int count = 4 * lanes;
+                std::copy(idx.begin() + first, idx.begin() + first + count, li);
+                std::copy(w.vals.begin() + first, w.vals.begin() + first + count, lv);
+                deal_chunk(lanes, [&](int k) { return (unsigned)li[k]; },
+                           [&](int slot, int k) { oi[slot] = li[k]; ov[slot] = lv[k]; });
+                std::copy(oi, oi + count, idx.begin() + first);
+                std::copy(ov, ov + count, w.vals.begin() + first);
+            }
+    };
+    const int n_threads = w.groups < 4096 ? 1 : pack_threads(L);
+    if (n_threads == 1) { deal_lists(0, L); return; }
+    // ranges of about equal group counts (lists may be very uneven: config 4)
+    std::vector<int64_t> cut((size_t)n_threads + 1, L);
+    cut[0] = 0;
+    int64_t c = 0;
+    for (int t = 1; t < n_threads; t++) {
+        const int64_t target = w.groups * t / n_threads;
+        while (c < L && (int64_t)w.colptr[c] < target) c++;
+        cut[(size_t)t] = c;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; t++) pool.emplace_back(deal_lists, cut[(size_t)t], cut[(size_t)t + 1]);
+    for (std::thread &th : pool) th.join();
 }
 
 static void wsp_bank_order(HostWsp &w)
@@ -371,9 +395,7 @@ int pack_panel(int64_t M, int64_t N, bool tiled, int W, bool lane_owned, const S
     P.vals.clear(); P.idx8.clear(); P.idx16.clear(); P.rel.clear();
     const int64_t per_slab = lane_owned ? (P.lob_blocks + 1) : tiled ? (P.row_blocks + 1) : (M + 1);
 
-    int n_threads = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
-    if (const char *e = std::getenv("SPMV_PACK_THREADS")) n_threads = std::max(1, std::atoi(e));
-    n_threads = std::max(1, std::min(n_threads, P.slabs));
+    const int n_threads = pack_threads(P.slabs);
     std::vector<SlabOut> outs((size_t)P.slabs);
     std::vector<RowStats> stats((size_t)n_threads);
     for (RowStats &st : stats) { st.nnz.assign((size_t)M, 0); st.groups.assign((size_t)M, 0); st.segs.assign((size_t)M, 0); }
