@@ -78,7 +78,11 @@ typedef struct spmv_options {
     int32_t  chunk_mode;     /* awsp/tcsr: 0 = auto, 1 = one row per 32-group chunk, 2 = short rows packed into shared chunks,
                                 3 = lane-owned blocks: for very sparse matrices (segments of a few non-zeros) whose
                                 activations are mostly non-zero — every stored non-zero is read, x is a multiplier,
-                                and a chunk retires in one pass (host packer only; slab_cols 1024..4096, default 2048) */
+                                and a chunk retires in one pass (host packer only; slab_cols 1024..4096, default 2048),
+                                4 = row strips (awsp only): very sparse matrices (about 1 % dense) — 8-byte entries,
+                                one row segment per 32-lane window, rows with x == 0 are never read; slab_cols then
+                                means columns per strip (multiple of 32, 32..2112; 0 = about 20 non-zeros per row
+                                and strip); host packer only */
     int32_t  pack_mode;      /* dense input: 0 = auto, 1 = pack on the host, 2 = pack on the GPU (the dense matrix is
                                 staged in HBM first; needs M*N*4 bytes of spare device memory).  Both give the
                                 same bytes. */
@@ -248,6 +252,44 @@ SPMV_API size_t spmv_compact_x_scratch_bytes(int64_t M);
  */
 SPMV_API int spmv_partition_columns(int64_t N, int parts, int64_t align, const int64_t *col_ptr,
                            int64_t *bounds /* parts+1 */);
+
+/* ---- column-sharded groups: several slabs per GPU, several GPUs ------------------------------- */
+/*
+ * SURVEY section 8e / BASELINE config 5 (the reference is single-GPU, one matrix per launcher call,
+ * e.g. awsp.cu:319-388).  A group describes one rank's share of a column-sharded matrix: its
+ * plans (each a slab of columns at a column offset of the full y) and the shared block that holds
+ * two alternating copies of the full y plus the arrival flags.  spmv_mg_run launches the rank's
+ * plans back to back; their epilogues store into EVERY rank's y (spmv_run_scatter), and a one-warp
+ * arrival kernel replaces the all-gather's synchronisation: it publishes this rank's epoch to all
+ * peers and waits for theirs on the device (no host round trip; CUDA-graph capturable — capture an
+ * even number of calls, the y buffers alternate).  With world == 1 it is simply "several slabs,
+ * one y".  No reduction crosses ranks: results are bit-identical to running the slabs alone.
+ *
+ *   one process per GPU    spmv_mg_create(NULL block) on every rank, exchange spmv_mg_ipc_handle()
+ *                          bytes through the caller's own transport (torch.distributed, MPI, a
+ *                          file), spmv_mg_connect_ipc();  or allocate the blocks as symmetric memory
+ *                          (spmv_mg_block_bytes), pass this rank's block to spmv_mg_create and all
+ *                          ranks' mappings (+ the NVSwitch multicast alias, if any) to
+ *                          spmv_mg_connect_ptrs();
+ *   one process, n GPUs    spmv_mg_create_group() (peer access), spmv_mg_group_run_host().
+ */
+typedef struct spmv_mg spmv_mg_t;   /* opaque */
+SPMV_API size_t spmv_mg_block_bytes(int64_t N_total);
+SPMV_API int  spmv_mg_create(int64_t M, int64_t N_total, int rank, int world, void *local_block, spmv_mg_t **out);
+SPMV_API void spmv_mg_destroy(spmv_mg_t *mg);
+SPMV_API int  spmv_mg_ipc_handle(spmv_mg_t *mg, void *handle64 /* 64 bytes out */);
+SPMV_API int  spmv_mg_connect_ipc(spmv_mg_t *mg, const void *handles /* world x 64 bytes, rank order */);
+SPMV_API int  spmv_mg_connect_ptrs(spmv_mg_t *mg, void *const *blocks /* world */, void *multicast_block /* or NULL */);
+/* plan: a slab of plan->N columns at col_offset (multiple of 4) of the full y; the caller keeps ownership */
+SPMV_API int  spmv_mg_add_plan(spmv_mg_t *mg, spmv_plan_t *plan, int64_t col_offset);
+/* asynchronous on `stream`; *d_y = this rank's copy of the full y, complete when the stream reaches this point */
+SPMV_API int  spmv_mg_run(spmv_mg_t *mg, const float *d_x, void *stream, const float **d_y);
+/* H2D x, spmv_mg_run, D2H y[y_begin, y_begin + y_count), synchronise (y_count = 0: no copy back) */
+SPMV_API int  spmv_mg_run_host(spmv_mg_t *mg, const float *x, float *y, int64_t y_begin, int64_t y_count);
+/* SPMV_OK, or SPMV_ERR_CUDA if an arrival wait timed out (a peer died); synchronous */
+SPMV_API int  spmv_mg_status(spmv_mg_t *mg);
+SPMV_API int  spmv_mg_create_group(int64_t M, int64_t N_total, int n_dev, const int *devices, spmv_mg_t **out /* n_dev */);
+SPMV_API int  spmv_mg_group_run_host(spmv_mg_t *const *groups, int n_dev, const float *x, float *y /* N_total */);
 
 /* ---- device-format inspection (host only; no GPU needed) ---------------------------------- */
 /*

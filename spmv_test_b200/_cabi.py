@@ -18,6 +18,9 @@ SYMBOLS = [
     "spmv_plan_traffic", "spmv_run", "spmv_run_act", "spmv_run_batch", "spmv_run_scatter", "spmv_run_host", "spmv_compact_x",
     "spmv_compact_x_scratch_bytes", "spmv_partition_columns", "spmv_ref_pack",
     "spmv_ref_packed_free", "spmv_pack_dump_dense", "spmv_pack_dump_csc", "spmv_pack_dump_free",
+    "spmv_mg_block_bytes", "spmv_mg_create", "spmv_mg_destroy", "spmv_mg_ipc_handle", "spmv_mg_connect_ipc",
+    "spmv_mg_connect_ptrs", "spmv_mg_add_plan", "spmv_mg_run", "spmv_mg_run_host", "spmv_mg_status",
+    "spmv_mg_create_group", "spmv_mg_group_run_host",
 ]
 
 
@@ -102,6 +105,20 @@ def lib():
     L.spmv_pack_dump_csc.argtypes = [i32, i64, i64, vp, vp, vp, C.POINTER(Options), C.POINTER(PackedDump)]
     L.spmv_pack_dump_free.argtypes = [C.POINTER(PackedDump)]
     L.spmv_pack_dump_free.restype = None
+    L.spmv_mg_block_bytes.argtypes = [i64]
+    L.spmv_mg_block_bytes.restype = C.c_size_t
+    L.spmv_mg_create.argtypes = [i64, i64, i32, i32, vp, C.POINTER(vp)]
+    L.spmv_mg_destroy.argtypes = [vp]
+    L.spmv_mg_destroy.restype = None
+    L.spmv_mg_ipc_handle.argtypes = [vp, vp]
+    L.spmv_mg_connect_ipc.argtypes = [vp, vp]
+    L.spmv_mg_connect_ptrs.argtypes = [vp, C.POINTER(vp), vp]
+    L.spmv_mg_add_plan.argtypes = [vp, vp, i64]
+    L.spmv_mg_run.argtypes = [vp, vp, vp, C.POINTER(vp)]
+    L.spmv_mg_run_host.argtypes = [vp, vp, vp, i64, i64]
+    L.spmv_mg_status.argtypes = [vp]
+    L.spmv_mg_create_group.argtypes = [i64, i64, i32, C.POINTER(i32), C.POINTER(vp)]
+    L.spmv_mg_group_run_host.argtypes = [C.POINTER(vp), i32, vp, vp]
     if L.spmv_abi_version() != 1:
         raise RuntimeError("libspmv_b200.so ABI version mismatch")
     _lib = L

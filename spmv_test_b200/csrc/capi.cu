@@ -162,14 +162,33 @@ static int setup_panel(spmv_plan *p, HostPanel &h, const spmv_options_t *o)
     return rc;
 }
 
+static int setup_strips(spmv_plan *p, HostStrips &h, const spmv_options_t *o)
+{
+    p->nnz = h.nnz; p->fmt_groups = 0;
+    int rc = upload(p, &p->strips.soff, h.soff);
+    p->off_bytes = (int64_t)h.soff.size() * 4;
+    if (!rc) {                                             // + 32 spare entries: an idle lane's (unread) source address stays legal
+        h.ent.resize(h.ent.size() + 32, 0);
+        rc = upload(p, reinterpret_cast<uint64_t **>(&p->strips.ent), h.ent);
+        h.ent.resize(h.ent.size() - 32);
+    }
+    if (!rc) rc = configure_strips(p, h, o);
+    p->row_nnz.swap(h.row_nnz);
+    return rc;
+}
+
+// chunk_mode 4 (row strips) applies to the awsp variant; slab_cols then means columns per strip
+static bool want_strips(const spmv_options_t *o, int variant) { return o && o->chunk_mode == 4 && variant == SPMV_AWSP; }
+
 static bool opts_ok(const spmv_options_t *o)
 {
     if (!o) return true;
     if (o->struct_size != sizeof(spmv_options_t)) return false;
     if (o->row_splits < 0 || o->warps_per_col < 0) return false;
     if (o->index_bits != 0 && o->index_bits != 16 && o->index_bits != 32) return false;
-    if (o->chunk_mode < 0 || o->chunk_mode > 3) return false;
+    if (o->chunk_mode < 0 || o->chunk_mode > 4) return false;
     if (o->pack_mode < 0 || o->pack_mode > 2) return false;
+    if (o->chunk_mode == 4) return o->slab_cols == 0 || (o->slab_cols >= 32 && o->slab_cols <= kMaxStripCols && o->slab_cols % 32 == 0);
     if (o->slab_cols != 0 && (o->slab_cols < kMinSlabCols || o->slab_cols > kMaxSlabCols || (o->slab_cols & (o->slab_cols - 1))))
         return false;
     return true;
@@ -283,7 +302,7 @@ static bool pack_on_device(const spmv_options_t *opts, int variant, int64_t M, i
 {
     if (M <= 0 || N <= 0 || variant == SPMV_ASP) return false;
     const int mode = opts ? opts->pack_mode : 0;
-    if (opts && opts->chunk_mode == 3 && variant != SPMV_WSP) return false;   // lane-owned blocks: host packer only
+    if (opts && opts->chunk_mode >= 3 && variant != SPMV_WSP) return false;   // lane-owned blocks, row strips: host packers only
     if (mode == 1) return false;
     if (mode == 2) return true;
     size_t free_b = 0, total_b = 0;
@@ -324,6 +343,11 @@ int spmv_plan_create_dense(int variant, int64_t M, int64_t N, const float *A, in
             }
             p->device_bytes += M * N * 4;
             if (!rc) rc = configure_asp(p, opts);
+        } else if (want_strips(opts, variant)) {
+            HostStrips h;
+            rc = pack_strips_dense(M, N, A, lda, opts->slab_cols, h);
+            if (rc) set_error(rc, "strips: cannot pack (strip width or size limits)");
+            else rc = setup_strips(p, h, opts);
         } else {
             HostPanel h;
             rc = pack_panel_dense(M, N, A, lda, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h,
@@ -355,8 +379,8 @@ int spmv_plan_create_dense_device(int variant, int64_t M, int64_t N, const float
         }
     }
     if (M <= 0 || N <= 0) return spmv_plan_create_dense(variant, M, N, nullptr, lda, opts, out);   // nothing to pack
-    if (opts && opts->chunk_mode == 3 && (variant == SPMV_AWSP || variant == SPMV_TCSR))
-        return set_error(SPMV_ERR_UNSUPPORTED, "lane-owned blocks (chunk_mode 3) are packed on the host: use spmv_plan_create_dense/_csc");
+    if (opts && opts->chunk_mode >= 3 && (variant == SPMV_AWSP || variant == SPMV_TCSR))
+        return set_error(SPMV_ERR_UNSUPPORTED, "lane-owned blocks and row strips (chunk_mode 3, 4) are packed on the host: use spmv_plan_create_dense/_csc");
     spmv_plan *p = nullptr;
     int rc = plan_begin(variant, M, N, &p);
     if (rc) return rc;
@@ -390,6 +414,11 @@ int spmv_plan_create_csc(int variant, int64_t M, int64_t N, const int64_t *col_p
             rc = pack_wsp_csc(M, N, col_ptr, row_idx, values, opts ? opts->index_bits : 0, w);
             if (rc) set_error(rc, "wsp: cannot pack (row index out of range, index width or size limits)");
             else rc = setup_wsp(p, w, opts);
+        } else if (want_strips(opts, variant)) {
+            HostStrips h;
+            rc = pack_strips_csc(M, N, col_ptr, row_idx, values, opts->slab_cols, h);
+            if (rc) set_error(rc, "strips: cannot pack (row index out of range, repeated entry, strip width or size limits)");
+            else rc = setup_strips(p, h, opts);
         } else {
             HostPanel h;
             rc = pack_panel_csc(M, N, col_ptr, row_idx, values, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h,
@@ -450,8 +479,14 @@ int spmv_plan_save(const spmv_plan_t *p, const char *path)
 {
     if (!p || !path) return set_error(SPMV_ERR_ARG, "null argument");
     int rc = SPMV_OK;
-    HostWsp w; HostPanel h; std::vector<float> dense;
-    if (p->variant == SPMV_WSP) {
+    HostWsp w; HostPanel h; HostStrips hs; std::vector<float> dense;
+    const bool strips = p->strips.strip_cols > 0;
+    if (strips) {
+        hs.M = p->M; hs.N = p->N; hs.nnz = p->nnz; hs.strip_cols = p->strips.strip_cols; hs.bands = p->strips.bands;
+        rc = fetch(hs.soff, p->strips.soff, (size_t)hs.bands * p->M * kStripsPerBand + 1);
+        if (!rc) rc = fetch(hs.ent, p->strips.ent, (size_t)hs.nnz);
+        hs.row_nnz = p->row_nnz;
+    } else if (p->variant == SPMV_WSP) {
         w.M = p->M; w.N = p->N; w.nnz = p->nnz; w.groups = p->fmt_groups; w.index_bits = p->wsp.index_bits;
         w.panels = p->wsp.panels; w.panel_rows = p->wsp.panel_rows;
         rc = fetch(w.colptr, p->wsp.colptr, (size_t)w.panels * p->N + 1);
@@ -482,6 +517,9 @@ int spmv_plan_save(const spmv_plan_t *p, const char *path)
         fw.vec(w.colptr); fw.vec(w.vals); fw.vec(w.idx16); fw.vec(w.idx32);
     } else if (p->variant == SPMV_ASP) {
         fw.vec(dense);
+    } else if (strips) {                                  // marked by a group count of -1
+        fw.pod<int64_t>(-1); fw.pod<int32_t>(hs.strip_cols); fw.pod<int32_t>(hs.bands);
+        fw.vec(hs.soff); fw.vec(hs.ent); fw.vec(hs.row_nnz);
     } else {
         fw.pod<int64_t>(h.groups); fw.pod<int32_t>(h.slab_cols); fw.pod<int32_t>(h.index_bits); fw.pod<int32_t>(h.slabs);
         fw.pod<int32_t>(h.row_blocks); fw.pod<int32_t>(h.tiled ? 1 : 0); fw.pod<int32_t>(h.block_rows);
@@ -554,7 +592,37 @@ int spmv_plan_load(const char *path, const spmv_options_t *opts, spmv_plan_t **o
         } else if (variant == SPMV_AWSP || variant == SPMV_TCSR) {
             HostPanel h; h.M = M; h.N = N; h.nnz = nnz;
             int32_t sc = 0, ib = 0, slabs = 0, rb = 0, tiled = 0, br = 0;
-            fr.pod(h.groups); fr.pod(sc); fr.pod(ib); fr.pod(slabs); fr.pod(rb); fr.pod(tiled); fr.pod(br);
+            fr.pod(h.groups);
+            if (fr.ok && h.groups == -1 && variant == SPMV_AWSP) {          // row strips
+                HostStrips hs; hs.M = M; hs.N = N; hs.nnz = nnz;
+                int32_t sw = 0, bands = 0;
+                fr.pod(sw); fr.pod(bands);
+                hs.strip_cols = sw; hs.bands = bands;
+                fr.vec(hs.soff); fr.vec(hs.ent); fr.vec(hs.row_nnz);
+                uint64_t tail = 0; fr.pod(tail);
+                const bool sane = fr.ok && tail == kFileMagic && sw >= 32 && sw <= kMaxStripCols && sw % 32 == 0 && nnz >= 0 &&
+                                  bands == (int32_t)std::max<int64_t>(1, (N + (int64_t)sw * kStripsPerBand - 1) / ((int64_t)sw * kStripsPerBand)) &&
+                                  hs.soff.size() == (size_t)bands * M * kStripsPerBand + 1 && hs.ent.size() == (size_t)nnz &&
+                                  hs.row_nnz.size() == (size_t)M && hs.soff.back() == (uint32_t)nnz && hs.soff.front() == 0u;
+                if (!sane) return fail("corrupt strips plan file");
+                for (size_t i = 0; i + 1 < hs.soff.size(); i++) {
+                    if (hs.soff[i] > hs.soff[i + 1]) return fail("corrupt strips plan file (offsets)");
+                    // columns inside the strip, strictly ascending inside a segment (distinct accumulators)
+                    for (uint32_t k = hs.soff[i]; k < hs.soff[i + 1]; k++) {
+                        const uint32_t c = (uint32_t)(hs.ent[k] >> 32);          // column + 1
+                        if (c == 0u || c > (uint32_t)sw || (k > hs.soff[i] && c <= (uint32_t)(hs.ent[k - 1] >> 32)))
+                            return fail("corrupt strips plan file (column ids)");
+                    }
+                }
+                fclose(f); f = nullptr;
+                rc = plan_begin(variant, M, N, &p);
+                if (!rc) rc = setup_strips(p, hs, opts);
+                if (!rc) rc = plan_finish(p);
+                if (rc) { if (p) spmv_plan_destroy(p); return rc; }
+                *out = p;
+                return SPMV_OK;
+            }
+            fr.pod(sc); fr.pod(ib); fr.pod(slabs); fr.pod(rb); fr.pod(tiled); fr.pod(br);
             h.slab_cols = sc; h.index_bits = ib; h.slabs = slabs; h.row_blocks = rb; h.tiled = tiled != 0;
             const bool lob = br != 0;
             if (lob) {
@@ -617,10 +685,10 @@ int spmv_plan_info(const spmv_plan_t *p, spmv_plan_info_t *info)
     info->grid_x = (int)p->grid.x; info->grid_y = (int)p->grid.y; info->block = p->block;
     info->smem_bytes = p->smem;
     info->index_bits = p->variant == SPMV_WSP ? p->wsp.index_bits
-                       : (p->variant == SPMV_ASP ? 0 : p->panel.index_bits);
+                       : (p->variant == SPMV_ASP ? 0 : p->strips.strip_cols > 0 ? 32 : p->panel.index_bits);
     info->row_splits = p->row_splits;
-    info->warps_per_col = p->variant == SPMV_WSP ? p->wsp.warps_per_col : (p->variant == SPMV_ASP ? 4 : p->panel.warps);
-    info->slab_cols = (p->variant == SPMV_AWSP || p->variant == SPMV_TCSR) ? p->panel.slab_cols : 0;
+    info->warps_per_col = p->variant == SPMV_WSP ? p->wsp.warps_per_col : (p->variant == SPMV_ASP ? 4 : p->strips.strip_cols > 0 ? kStripsPerBand : p->panel.warps);
+    info->slab_cols = (p->variant == SPMV_AWSP || p->variant == SPMV_TCSR) ? (p->strips.strip_cols > 0 ? p->strips.strip_cols : p->panel.slab_cols) : 0;
     return SPMV_OK;
 }
 
@@ -647,6 +715,15 @@ int spmv_plan_traffic(const spmv_plan_t *p, const float *x, double *alg_bytes, d
         touched = mnz * p->N;
         alg = 4.0 * mnz * N + vec;
         phys = alg + split_io;
+    } else if (p->strips.strip_cols > 0) {
+        // row strips: 8 bytes per entry of an active row, one 64-byte offset record per (band, active row),
+        // one partial band row per CTA written and read back
+        int64_t active = 0;
+        for (int64_t j = 0; j < p->M; j++)
+            if (x[j] != 0.0f) { touched += p->row_nnz[j]; active++; }
+        alg = 8.0 * touched + 4.0 * (N + 1) + vec;
+        const double part_io = p->strips.ctas_per_band > 1 ? 2.0 * 4.0 * (double)p->grid.x * p->tile_width : 0.0;
+        phys = 8.0 * touched + (double)active * p->strips.bands * kStripsPerBand * 4.0 + 4.0 * M * p->strips.bands + 4.0 * N + part_io;   // every band's CTAs read x once
     } else {
         int64_t groups = 0;
         for (int64_t j = 0; j < p->M; j++)
@@ -667,7 +744,7 @@ static int run_to(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t s
     case SPMV_WSP: return launch_wsp(p, d_x, yd, st);
     case SPMV_ASP: return launch_asp(p, d_x, yd, st);
     case SPMV_AWSP:
-    case SPMV_TCSR: return launch_panel(p, d_x, yd, st);
+    case SPMV_TCSR: return p->strips.strip_cols > 0 ? launch_strips(p, d_x, yd, st) : launch_panel(p, d_x, yd, st);
     }
     return set_error(SPMV_ERR_ARG, "corrupt plan");
 }

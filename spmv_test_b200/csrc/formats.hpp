@@ -88,4 +88,35 @@ struct HostPanel {
     std::vector<int32_t> row_segs;   // [M]  non-empty segments per row       — traffic accounting
 };
 
+// ------------------------------------------------------------------------------------------
+// Row strips (chunk_mode 4; very sparse matrices, e.g. BASELINE config 5 at 1 %): the form that
+// keeps both promises of the awsp variant when a row segment holds only a few non-zeros — a row
+// with x[row] == 0 is never read, and what IS read comes in DRAM-friendly pieces.
+//   * the N outputs are cut into strips of `strip_cols` columns (about 20 non-zeros per row and
+//     strip), kStripsPerBand = 16 consecutive strips form a band;
+//   * storage is band-major, row-minor, strip-minor: the 16 strip segments of one row of one band
+//     are contiguous (one 2-3 KB run per active row), so the unit DRAM sees is the band row while
+//     the unit a warp works on is its own strip of that row;
+//   * an entry is 8 bytes {fp32 value, u32 (column inside the strip) + 1}; inside a (row, strip)
+//     the entries are in ascending column order, so they are distinct accumulators; the all-zero
+//     entry (what a zero-filled copy produces for an idle lane) addresses accumulator 0, which no
+//     column uses;
+//   * soff[(band*M + row)*16 + strip] = first entry of the segment (32-bit; one sentinel at the end).
+// The kernel (strips.cu) gives a band's row range to a 16-warp CTA, warp w owns strip w: one
+// row segment = one 32-lane window, one entry per lane, no two lanes on one accumulator, so a
+// window retires in a single pass whatever its length.
+// ------------------------------------------------------------------------------------------
+constexpr int kStripsPerBand = 16;
+constexpr int kMaxStripCols = 2112;      // 16 x (strip accumulators + ring + row table) must fit 227 KB
+constexpr double kStripTargetNnz = 20.5; // mean non-zeros per (row, strip): P(> 32) stays under 1 %
+
+struct HostStrips {
+    int64_t M = 0, N = 0, nnz = 0;
+    int strip_cols = 0;
+    int bands = 0;
+    std::vector<uint64_t> ent;       // value bits | (uint64)(column + 1) << 32
+    std::vector<uint32_t> soff;      // bands*M*16 + 1
+    std::vector<int32_t> row_nnz;    // [M] stored nnz per row (all bands) — traffic accounting
+};
+
 } // namespace spmv

@@ -3,7 +3,7 @@
 //   (2) the reference's six host layouts, bit-exact, behind spmv_ref_pack() — what the drop-in
 //       format classes (host/formats.cpp) are made of.
 // Written from the layout descriptions in SURVEY.md §2a; checked bit-for-bit against the
-// reference packers through the oracle (tests/test_ref_layouts.py).
+// reference packers through the oracle (tests/test_oracle_pinned.py, tests/test_packers_cpu.py).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -494,6 +494,144 @@ int pack_panel_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *
     return pack_panel(M, N, tiled, slab_cols, lane_owned, src, P);
 }
 
+// ---------------------------------------------------------------------------- row strips ---
+// Strip width from the density: about kStripTargetNnz non-zeros per (row, strip), a whole number
+// of bands over N, a multiple of 32 columns, at most kMaxStripCols (shared-memory accumulators).
+int choose_strip_cols(int64_t M, int64_t N, int64_t nnz)
+{
+    if (M <= 0 || N <= 0 || nnz <= 0) return 32;
+    const double density = (double)nnz / ((double)M * (double)N);
+    const double want = std::min<double>(kMaxStripCols, std::max(32.0, kStripTargetNnz / density));
+    const int64_t bands = std::max<int64_t>(1, (int64_t)((double)N / (kStripsPerBand * want) + 0.5));
+    int64_t w = (N + bands * kStripsPerBand - 1) / (bands * kStripsPerBand);
+    w = (w + 31) / 32 * 32;
+    return (int)std::min<int64_t>(kMaxStripCols, std::max<int64_t>(32, w));
+}
+
+namespace {
+void strips_begin(int64_t M, int64_t N, int strip_cols, HostStrips &h)
+{
+    h.M = M; h.N = N; h.strip_cols = strip_cols;
+    const int64_t band_cols = (int64_t)strip_cols * kStripsPerBand;
+    h.bands = (int)std::max<int64_t>(1, (N + band_cols - 1) / band_cols);
+    h.soff.assign((size_t)h.bands * M * kStripsPerBand + 1, 0u);
+    h.row_nnz.assign((size_t)M, 0);
+}
+inline uint64_t strip_entry(float v, uint32_t col)       // column inside the strip, stored + 1 (formats.hpp)
+{
+    uint32_t bits;
+    std::memcpy(&bits, &v, 4);
+    return (uint64_t)bits | ((uint64_t)(col + 1u) << 32);
+}
+} // namespace
+
+int pack_strips_dense(int64_t M, int64_t N, const float *A, int64_t lda, int strip_cols, HostStrips &h)
+{
+    if (strip_cols <= 0) {
+        int64_t nnz = 0;
+        for (int64_t j = 0; j < M; j++) {
+            const float *row = A + j * lda;
+            for (int64_t i = 0; i < N; i++) nnz += (row[i] != 0.0f);
+        }
+        strip_cols = choose_strip_cols(M, N, nnz);
+    }
+    if (strip_cols < 32 || strip_cols > kMaxStripCols || strip_cols % 32) return SPMV_ERR_ARG;
+    strips_begin(M, N, strip_cols, h);
+    const int64_t band_cols = (int64_t)strip_cols * kStripsPerBand;
+    h.ent.clear();
+    size_t seg = 0;
+    for (int b = 0; b < h.bands; b++)
+        for (int64_t j = 0; j < M; j++) {
+            const float *row = A + j * lda;
+            for (int s = 0; s < kStripsPerBand; s++, seg++) {
+                if (h.ent.size() >= (size_t)UINT32_MAX) return SPMV_ERR_UNSUPPORTED;
+                h.soff[seg] = (uint32_t)h.ent.size();
+                const int64_t c0 = b * band_cols + (int64_t)s * strip_cols;
+                const int64_t c1 = std::min<int64_t>(N, c0 + strip_cols);
+                for (int64_t c = c0; c < c1; c++)
+                    if (row[c] != 0.0f) { h.ent.push_back(strip_entry(row[c], (uint32_t)(c - c0))); h.row_nnz[(size_t)j]++; }
+            }
+        }
+    if (h.ent.size() >= (size_t)UINT32_MAX) return SPMV_ERR_UNSUPPORTED;
+    h.soff[seg] = (uint32_t)h.ent.size();
+    h.nnz = (int64_t)h.ent.size();
+    return SPMV_OK;
+}
+
+// From CSR(A^T): per band a counting sort of its entries by (row, strip); columns are visited in
+// ascending order, so the entries of a segment come out in ascending column order.  Bands are
+// independent: a small pool of host threads takes them (same bytes for any thread count).
+int pack_strips_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx, const float *values,
+                    int strip_cols, HostStrips &h)
+{
+    int64_t nnz = 0;
+    for (int64_t k = col_ptr[0]; k < col_ptr[N]; k++) {
+        if (row_idx[k] < 0 || row_idx[k] >= M) return SPMV_ERR_ARG;
+        nnz += (values[k] != 0.0f);
+    }
+    if (nnz >= (int64_t)UINT32_MAX) return SPMV_ERR_UNSUPPORTED;
+    if (strip_cols <= 0) strip_cols = choose_strip_cols(M, N, nnz);
+    if (strip_cols < 32 || strip_cols > kMaxStripCols || strip_cols % 32) return SPMV_ERR_ARG;
+    strips_begin(M, N, strip_cols, h);
+    h.nnz = nnz;
+    h.ent.assign((size_t)nnz, 0);
+    const int64_t band_cols = (int64_t)strip_cols * kStripsPerBand;
+    const size_t per_band = (size_t)M * kStripsPerBand;
+    // entries per band -> the band's first entry
+    std::vector<int64_t> band_first((size_t)h.bands + 1, 0);
+    for (int b = 0; b < h.bands; b++) {
+        int64_t n = 0;
+        const int64_t c1 = std::min<int64_t>(N, (b + 1) * band_cols);
+        for (int64_t c = b * band_cols; c < c1; c++)
+            for (int64_t k = col_ptr[c]; k < col_ptr[c + 1]; k++) n += (values[k] != 0.0f);
+        band_first[(size_t)b + 1] = band_first[(size_t)b] + n;
+    }
+    const int n_threads = pack_threads(h.bands);
+    std::vector<std::vector<int32_t>> rn((size_t)n_threads);
+    int dup_rc = SPMV_OK;
+    auto worker = [&](int t) {
+        std::vector<int32_t> &row_cnt = rn[(size_t)t];
+        row_cnt.assign((size_t)M, 0);
+        std::vector<uint32_t> cur(per_band);
+        for (int b = t; b < h.bands; b += n_threads) {
+            uint32_t *so = h.soff.data() + (size_t)b * per_band;
+            std::fill(cur.begin(), cur.end(), 0u);
+            const int64_t cb = b * band_cols, c1 = std::min<int64_t>(N, cb + band_cols);
+            for (int64_t c = cb; c < c1; c++) {
+                const int s = (int)((c - cb) / strip_cols);
+                for (int64_t k = col_ptr[c]; k < col_ptr[c + 1]; k++)
+                    if (values[k] != 0.0f) cur[(size_t)row_idx[k] * kStripsPerBand + s]++;
+            }
+            uint32_t run = (uint32_t)band_first[(size_t)b];
+            for (size_t i = 0; i < per_band; i++) { const uint32_t n = cur[i]; so[i] = run; cur[i] = run; run += n; }
+            for (int64_t c = cb; c < c1; c++) {
+                const int s = (int)((c - cb) / strip_cols);
+                const uint32_t lc = (uint32_t)(c - cb - (int64_t)s * strip_cols);
+                for (int64_t k = col_ptr[c]; k < col_ptr[c + 1]; k++)
+                    if (values[k] != 0.0f) {
+                        const size_t seg = (size_t)row_idx[k] * kStripsPerBand + s;
+                        const uint32_t p = cur[seg]++;
+                        // a repeated (row, column) pair would put two entries of one window on one accumulator
+                        if (p > so[seg] && (uint32_t)(h.ent[p - 1] >> 32) == lc + 1u) dup_rc = SPMV_ERR_ARG;
+                        h.ent[p] = strip_entry(values[k], lc);
+                        row_cnt[(size_t)row_idx[k]]++;
+                    }
+            }
+        }
+    };
+    if (n_threads == 1) worker(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_threads; t++) pool.emplace_back(worker, t);
+        for (std::thread &th : pool) th.join();
+    }
+    if (dup_rc) return dup_rc;
+    h.soff.back() = (uint32_t)nnz;
+    for (const std::vector<int32_t> &v : rn)
+        for (int64_t r = 0; r < M; r++) h.row_nnz[(size_t)r] += v[(size_t)r];
+    return SPMV_OK;
+}
+
 } // namespace spmv
 
 // ==========================================================================================
@@ -726,6 +864,24 @@ void dump_panel(const spmv::HostPanel &h, int variant, spmv_packed_dump_t *o)
     if (h.tiled) { o->rel = dup_vec(h.rel); o->n_rel = (int64_t)h.rel.size(); }
 }
 
+// row strips: vals / idx (u32 column inside the strip) per entry, off = soff, slab_cols = columns per
+// strip, slabs = bands, row_blocks = strips per band, block_rows = -1 marks the form
+void dump_strips(const spmv::HostStrips &h, spmv_packed_dump_t *o)
+{
+    o->variant = SPMV_AWSP; o->index_bits = 32; o->slab_cols = h.strip_cols; o->slabs = h.bands;
+    o->row_blocks = spmv::kStripsPerBand; o->block_rows = -1; o->M = h.M; o->N = h.N; o->nnz = h.nnz; o->groups = 0;
+    std::vector<float> v(h.ent.size());
+    std::vector<uint32_t> c(h.ent.size());
+    for (size_t k = 0; k < h.ent.size(); k++) {
+        const uint32_t bits = (uint32_t)h.ent[k];
+        std::memcpy(&v[k], &bits, 4);
+        c[k] = (uint32_t)(h.ent[k] >> 32) - 1u;               // the dump shows plain column numbers
+    }
+    o->vals = dup_vec(v); o->n_vals = (int64_t)v.size();
+    o->idx = dup_vec(c); o->idx_bytes = (int64_t)c.size() * 4;
+    o->off = dup_vec(h.soff); o->n_off = (int64_t)h.soff.size();
+}
+
 int dump_common_check(int variant, int64_t M, int64_t N, spmv_packed_dump_t *out)
 {
     if (!out) return spmv::set_error(SPMV_ERR_ARG, "null output");
@@ -748,6 +904,10 @@ extern "C" int spmv_pack_dump_dense(int variant, int64_t M, int64_t N, const flo
             spmv::HostWsp w;
             rc = spmv::pack_wsp_dense(M, N, A, lda, opts ? opts->index_bits : 0, w);
             if (!rc) dump_wsp(w, out);
+        } else if (opts && opts->chunk_mode == 4 && variant == SPMV_AWSP) {
+            spmv::HostStrips h;
+            rc = spmv::pack_strips_dense(M, N, A, lda, opts->slab_cols, h);
+            if (!rc) dump_strips(h, out);
         } else {
             spmv::HostPanel h;
             rc = spmv::pack_panel_dense(M, N, A, lda, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h,
@@ -771,6 +931,10 @@ extern "C" int spmv_pack_dump_csc(int variant, int64_t M, int64_t N, const int64
             spmv::HostWsp w;
             rc = spmv::pack_wsp_csc(M, N, col_ptr, row_idx, values, opts ? opts->index_bits : 0, w);
             if (!rc) dump_wsp(w, out);
+        } else if (opts && opts->chunk_mode == 4 && variant == SPMV_AWSP) {
+            spmv::HostStrips h;
+            rc = spmv::pack_strips_csc(M, N, col_ptr, row_idx, values, opts->slab_cols, h);
+            if (!rc) dump_strips(h, out);
         } else {
             spmv::HostPanel h;
             rc = spmv::pack_panel_csc(M, N, col_ptr, row_idx, values, variant == SPMV_TCSR, opts ? opts->slab_cols : 0, h,

@@ -54,6 +54,10 @@ int pack_panel_dense(int64_t M, int64_t N, const float *A, int64_t lda, bool til
 int pack_panel_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx,
                    const float *values, bool tiled, int slab_cols, HostPanel &P, bool lane_owned = false);
 int choose_slab_cols(int64_t M, int64_t N, int64_t nnz);
+int pack_strips_dense(int64_t M, int64_t N, const float *A, int64_t lda, int strip_cols, HostStrips &h);
+int pack_strips_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx, const float *values,
+                    int strip_cols, HostStrips &h);
+int choose_strip_cols(int64_t M, int64_t N, int64_t nnz);
 void wsp_choose_panels(HostWsp &w, int64_t nnz, int index_bits_opt);   // sets panels, panel_rows, index_bits
 
 struct DevWsp {
@@ -90,6 +94,15 @@ struct DevPanel {
     int lob_blocks = 0;
 };
 
+// row strips (formats.hpp: HostStrips; strips.cu)
+struct DevStrips {
+    uint2 *ent = nullptr;
+    uint32_t *soff = nullptr;
+    int strip_cols = 0;         // > 0: the plan is in the row-strip form
+    int bands = 0;
+    int ctas_per_band = 1;
+};
+
 } // namespace spmv
 
 struct spmv_plan {
@@ -105,6 +118,7 @@ struct spmv_plan {
     int wsp_team = 0;
     spmv::DevAsp asp;
     spmv::DevPanel panel;
+    spmv::DevStrips strips;
 
     // split-reduction scratch (asp/awsp/tcsr)
     int row_splits = 1;
@@ -145,6 +159,7 @@ int launch_wsp_batch(spmv_plan *p, const float *d_x, long long ldx, const YDst &
 int launch_asp(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
 int launch_asp_batch(spmv_plan *p, const float *d_x, long long ldx, const YDst &yd, long long ldy, int B, cudaStream_t st);
 int launch_panel(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
+int launch_strips(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
 int launch_compact(const float *d_x, int64_t M, int32_t *d_idx, float *d_val, int32_t *d_count,
                    void *d_scratch, size_t scratch_bytes, cudaStream_t st);
 size_t compact_scratch_bytes(int64_t M);
@@ -152,6 +167,7 @@ size_t compact_scratch_bytes(int64_t M);
 int configure_wsp(spmv_plan *p, const HostWsp &w, const spmv_options_t *o);
 int configure_asp(spmv_plan *p, const spmv_options_t *o);
 int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o);
+int configure_strips(spmv_plan *p, const HostStrips &h, const spmv_options_t *o);
 void destroy_wsp_state(spmv_plan *p);
 int clone_wsp_state(const spmv_plan *src, spmv_plan *dst);
 int alloc_split_scratch(spmv_plan *p, int copies = 1);   // partial + tickets from row_splits/col_tiles/tile_width (x copies)

@@ -574,3 +574,75 @@ def test_fused_relu_and_ffn_chain(S):
     with pytest.raises(S.SpmvError):
         with S.Plan.from_dense("asp", A1) as p:
             p.run(dx, torch.empty(H, device="cuda"), act=7)
+
+
+# ---- row strips (chunk_mode 4) ---------------------------------------------------------------------
+STRIP_SHAPES = [
+    # M, N, weight sparsity, activation sparsity, strip columns (0 = from the density)
+    (32, 32, 0.5, 0.5, 0), (1, 64, 0.0, 0.0, 32), (1000, 512, 0.7, 0.5, 32), (2049, 2048 + 96, 0.98, 0.5, 0),
+    (5000, 4096, 0.99, 0.5, 0), (3000, 8192, 0.995, 0.0, 2112), (70000, 512, 0.99, 0.9, 0), (4100, 4096, 0.9, 0.5, 128),
+    (300, 40000, 0.99, 0.3, 0),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,sa,sx,sw", STRIP_SHAPES)
+def test_row_strips_parity(S, M, N, sa, sx, sw, tmp_path):
+    """chunk_mode 4: one row segment per 32-lane window, rows with x == 0 never read; same parity bar,
+    and the CSR(A^T) route, a saved plan, a clone and a scattered run give the same bits."""
+    import torch
+    A = ob.gen_matrix(M, N, sa, 1234)
+    if M > 40:
+        A[:, 3] = 0.25                                                   # a column every row touches
+        A[37, :] = 0.0                                                   # an empty row
+        A[38, :] = -0.5                                                  # a full row: segments longer than a window
+    x = ob.gen_vector(M, sx, 4321)
+    if M > 40:
+        x[38] = 0.75
+    kw = {"slab_cols": sw} if sw else {}
+    ys = run_all(S, A, x, variants=("awsp",), chunk_mode=4, **kw)
+    from scipy import sparse
+    c = sparse.csc_matrix(A)
+    with S.Plan.from_csc("awsp", M, N, c.indptr.astype(np.int64), c.indices.astype(np.int32), c.data.astype(np.float32),
+                         chunk_mode=4, **kw) as p:
+        assert p.run_host(x).tobytes() == ys["awsp"].tobytes()
+        p.save(tmp_path / "strips.plan")
+        with p.clone() as q:
+            assert q.run_host(x).tobytes() == ys["awsp"].tobytes()
+        alg, phys, touched = p.traffic(x)
+        assert touched == int(np.count_nonzero(A[x != 0.0])) and phys > 0
+        # the scatter epilogue (multi-GPU path) through the same kernels
+        bufs = [torch.full((N + 64,), -7.0, device="cuda") for _ in range(2)]
+        p.run_scatter(torch.from_numpy(x).cuda(), [b.data_ptr() for b in bufs], 32)
+        torch.cuda.synchronize()
+        for b in bufs:
+            assert b[32:32 + N].cpu().numpy().tobytes() == ys["awsp"].tobytes()
+            assert float(b[:32].max()) == -7.0 and float(b[32 + N:].max()) == -7.0
+        yr = torch.empty(N, device="cuda")
+        p.run(torch.from_numpy(x).cuda(), yr, act="relu")
+        torch.cuda.synchronize()
+        assert np.array_equal(yr.cpu().numpy(), np.where(ys["awsp"] < 0, np.float32(0), ys["awsp"]))
+    with S.Plan.load(tmp_path / "strips.plan") as q:
+        assert q.run_host(x).tobytes() == ys["awsp"].tobytes()
+    raw = bytearray((tmp_path / "strips.plan").read_bytes())
+    if len(raw) > 4000:
+        raw[len(raw) // 2] ^= 0xFF
+        (tmp_path / "bad.plan").write_bytes(bytes(raw[:-9]))
+        with pytest.raises(S.SpmvError):
+            S.Plan.load(tmp_path / "bad.plan")
+
+
+@pytest.mark.gpu
+def test_row_strips_row_ranges_and_zero_x(S):
+    """Forced CTAs per band (one: direct stores of y; many: the partial rows + the reduce kernel; more
+    rows than one compaction pass per CTA), an all-zero x, and x with a single active row."""
+    A = ob.gen_matrix(9000, 4096, 0.99, 77)
+    x = ob.gen_vector(9000, 0.5, 78)
+    outs = []
+    for o in (dict(), dict(row_splits=1), dict(row_splits=2), dict(row_splits=7), dict(row_splits=140)):
+        outs.append(run_all(S, A, x, variants=("awsp",), chunk_mode=4, **o)["awsp"])
+    x0 = np.zeros(9000, np.float32)
+    run_all(S, A, x0, variants=("awsp",), chunk_mode=4)
+    x1 = x0.copy(); x1[8999] = 2.0
+    y = run_all(S, A, x1, variants=("awsp",), chunk_mode=4)["awsp"]
+    assert np.array_equal(y, 2.0 * A[8999])

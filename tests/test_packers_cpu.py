@@ -216,3 +216,67 @@ def test_lane_owned_blocks_reject_narrow_slabs():
     for w in (256, 512):
         with pytest.raises(S.SpmvError):
             S.pack_dump("awsp", A, chunk_mode=3, slab_cols=w)
+
+
+# ---- row strips (chunk_mode 4) -------------------------------------------------------------------
+def _decode_strips(d):
+    """Rebuilds the dense matrix from a dumped row-strip image and checks the format's invariants."""
+    S16, sw, bands = d.row_blocks, d.slab_cols, d.slabs
+    assert d.block_rows == -1 and S16 == 16 and d.index_bits == 32 and sw % 32 == 0
+    assert bands == max(1, -(-d.N // (S16 * sw)))
+    assert d.off.size == bands * d.M * S16 + 1 and d.off[0] == 0 and d.off[-1] == d.vals.size == d.idx.size == d.nnz
+    assert np.all(np.diff(d.off.astype(np.int64)) >= 0)
+    A = np.zeros((d.M, bands * S16 * sw), np.float32)
+    seg = 0
+    for b in range(bands):
+        for row in range(d.M):
+            for s in range(S16):
+                e0, e1 = int(d.off[seg]), int(d.off[seg + 1])
+                seg += 1
+                c = d.idx[e0:e1].astype(np.int64)
+                assert np.all(c < sw) and np.all(np.diff(c) > 0), "columns of a segment ascend strictly"
+                A[row, (b * S16 + s) * sw + c] = d.vals[e0:e1]
+    assert not np.any(A[:, d.N:])
+    return A[:, :d.N]
+
+
+@pytest.mark.parametrize("shape,keep,sw", [((64, 64), 0.5, 32), ((100, 4096), 0.02, 0), ((37, 2048 + 96), 0.05, 64),
+                                           ((300, 1024), 0.3, 32), ((1, 32), 1.0, 0), ((0, 64), 0.5, 0)])
+def test_row_strips_hold_the_matrix(shape, keep, sw):
+    import spmv_test_b200 as S
+    from scipy import sparse
+    M, N = shape
+    A = ob.gen_matrix(M, N, 1.0 - keep, 99)
+    if M > 10:
+        A[5, :] = 0.0                                     # an empty row
+        A[7, :] = 1.5                                     # a full row: segments longer than a 32-lane window
+    kw = {"slab_cols": sw} if sw else {}
+    d = S.pack_dump("awsp", A, chunk_mode=4, **kw)
+    assert np.array_equal(_decode_strips(d), A)
+    assert d.nnz == int(np.count_nonzero(A))
+    if M:
+        c = sparse.csc_matrix(A)
+        d2 = S.pack_dump("awsp", csc=(c.indptr.astype(np.int64), c.indices.astype(np.int32), c.data.astype(np.float32)),
+                         shape=(M, N), chunk_mode=4, **kw)
+        for f in ("vals", "idx", "off"):
+            assert getattr(d, f).tobytes() == getattr(d2, f).tobytes(), f
+        assert d2.slab_cols == d.slab_cols
+
+
+def test_row_strips_width_rule_and_bad_input():
+    import spmv_test_b200 as S
+    from spmv_test_b200 import synth
+    # config-5-like density: ~20.5 non-zeros per (row, strip), whole bands over N
+    cp, ri, va = synth.bernoulli_csc(4096, 32768, 0.01, 5)
+    d = S.pack_dump("awsp", csc=(cp, ri, va), shape=(4096, 32768), chunk_mode=4)
+    assert d.slab_cols == 2048 and d.slabs == 1
+    per_seg = np.diff(d.off.astype(np.int64))
+    assert 19.5 < per_seg.mean() < 21.5 and (per_seg > 32).mean() < 0.01
+    with pytest.raises(S.SpmvError):                      # strip width must be a multiple of 32 up to the shared-memory limit
+        S.pack_dump("awsp", csc=(cp, ri, va), shape=(4096, 32768), chunk_mode=4, slab_cols=48)
+    with pytest.raises(S.SpmvError):
+        S.pack_dump("awsp", csc=(cp, ri, va), shape=(4096, 32768), chunk_mode=4, slab_cols=4096)
+    # a repeated (row, column) pair would put two entries of one window on one accumulator: rejected
+    cp2 = np.array([0, 2] + [2] * 31, np.int64)
+    with pytest.raises(S.SpmvError):
+        S.pack_dump("awsp", csc=(cp2, np.array([3, 3], np.int32), np.array([1.0, 2.0], np.float32)), shape=(8, 32), chunk_mode=4)

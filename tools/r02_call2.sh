@@ -1,0 +1,10 @@
+#!/bin/bash
+set -u
+O=gpurun_out
+mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -x -q -k "strips or smoke" > $O/c2_pytest.log 2>&1; echo "pytest rc=$?"
+tail -3 $O/c2_pytest.log
+timeout 300 python tools/c5_slab.py chunk_mode=4 > $O/c2_plain_strips.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:strips_kernel -s 3 -c 1 -o $O/r02_strips_v2 python tools/c5_slab.py chunk_mode=4 > $O/c2_ncu_strips.log 2>&1
+echo "ncu rc=$?"
+cat $O/c2_plain_strips.log
