@@ -40,8 +40,8 @@ harness: build/sparse_sgemv
 HOST_SRCS := $(wildcard $(HOST)/*.cpp) test/main.cpp
 build/sparse_sgemv: $(HOST_SRCS) $(wildcard $(HOST)/include/*.hpp) $(LIBDIR)/libspmv_b200.so
 	@mkdir -p build
-	$(CXX) -std=c++17 -O2 -I$(HOST)/include -Iinclude -o $@ $(HOST_SRCS) -L$(LIBDIR) -lspmv_b200 \
-	    -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
+	$(CXX) -std=c++17 -O2 -I$(HOST)/include -Iinclude -I$(CUDA)/include -o $@ $(HOST_SRCS) -L$(LIBDIR) -lspmv_b200 \
+	    -L$(CUDA)/lib64 -lcublas -lcudart -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)' -Wl,-rpath,$(CUDA)/lib64
 
 clean:
 	rm -rf build $(LIBDIR)/libspmv_b200.so

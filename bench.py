@@ -2,35 +2,35 @@
 """bench.py — sparse SGEMV Y = x·A on B200: µs/call and effective HBM GB/s vs the roofline.
 
     python bench.py --gpus N --steps K --warmup W          (N > 1: launched by torchrun)
-    python bench.py --impl reference ...                    (the reference's CPU path, rank 0)
+    python bench.py --impl reference ...                    (the CPU path, rank 0)
 
-N = 1   workload = BASELINE config 2 (LLM decode FFN up-proj: A 4096x14336, 70 % weight-sparse,
-        x 50 % activation-sparse).  The config names three variants (wsp; asp/awsp), so a step is
-        one call of each of them on the same A and x; every variant (and tcsr, and the other
-        single-GPU configs) is also timed alone and reported under "variants" / "configs", and
-        "roofline" describes the step's dominant (longest) kernel.
-N > 1   workload = BASELINE config 5 family, weak scaling: every rank owns a 131072-column slab
-        of A (65536 rows, 99 % sparse, built directly in sparse form; lane-owned block form of the
-        awsp format, chunk_mode 3), x is replicated, a step is the local awsp call whose epilogue
-        stores its slice of Y into every rank's buffer (fused all-gather; the NCCL all-gather join
-        is timed beside it, "join").  At N = 8 this is exactly config 5 (65536 x 1048576).  The N = 1 line also carries this slab's single-GPU number
-        ("weak_scaling_unit") so per-N efficiency can be computed on one workload.
+Workload at EVERY N (strong scaling): BASELINE config 5 — the fixed matrix A 65536 x 1048576, 99 %
+sparse, built directly in sparse form as eight 131072-column slabs (seeds 5000..5007), x 50 %
+activation-sparse, awsp variant in the row-strip form (chunk_mode 4).  Rank r owns the slabs
+[8r/N, 8(r+1)/N); a step is y = x·A for the whole matrix: every rank runs its slabs back to back,
+their epilogues store each slice of y into every rank's copy of y (fused all-gather) and a
+one-warp arrival kernel joins the ranks (spmv_mg_run).  At N = 1 the line also carries every
+other BASELINE config per variant ("configs"), each checked against the oracle.
 
-value   = algorithmic bytes (8*nnz_touched + 4(N+1) + 4M + 4N) of all ranks divided by
-          the device time of the timed region (CUDA events, max over ranks), in GB/s.
-L2      every timed loop rotates over clones of the packed matrix whose total size exceeds
-        2.5x the 126 MB L2, so each call streams from HBM (config.l2 says how many copies).
+value   = algorithmic bytes (8*nnz_touched + 4(N+1) + 4M + 4N) of the whole matrix divided
+          by the device time of a step (CUDA events on the launching stream, max over ranks), GB/s.
+L2      config 5: a rank's slabs are 0.7 GB (N = 8) .. 5.6 GB (N = 1), far beyond the 126 MB L2.
+          Small configs: every timed loop rotates over clones of the packed matrix whose total
+          size exceeds 2.5x L2; a hot-L2 figure (one copy) is reported separately.
+parity  every timed plan is first checked against the CPU oracle (tests/parity.py gate); a
+          failure makes the exit code non-zero.
 """
 from __future__ import annotations
 
 import argparse
-import ctypes as C
+import hashlib
 import json
 import os
 import statistics
 import sys
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -40,9 +40,11 @@ sys.path.insert(0, ROOT)
 METRIC = "sparse SGEMV Y=xA effective HBM throughput (algorithmic bytes / device time)"
 UNIT = "GB/s"
 L2_BYTES = 126e6
-HEADLINE = "awsp"                      # multi-GPU (config 5) variant
-STEP_VARIANTS = ("wsp", "asp", "awsp")   # config 2 names all three: one step = one call of each
-C5_M, C5_SLAB_N, C5_DENSITY, C5_SX = 65536, 131072, 0.01, 0.5
+HEADLINE = "awsp"
+C5_M, C5_SLAB_N, C5_SLABS, C5_DENSITY, C5_SX = 65536, 131072, 8, 0.01, 0.5
+C5_CHUNK_MODE = 4                       # row strips (strips.cu); 3 = lane-owned blocks, 0 = multi-row panel form
+C5_CHECK_COLS = 1024                    # oracle columns sampled per slab
+PARITY_FAILED = []
 
 
 def peaks():
@@ -61,6 +63,16 @@ def ncu_traffic(key):
             return json.load(f).get(key)
     except Exception:
         return None
+
+
+def oracle_bindings():
+    """The checker (test infrastructure): only the parity checks and the CPU baseline legs use it."""
+    t = os.path.join(ROOT, "tests")
+    if t not in sys.path:
+        sys.path.insert(0, t)
+    import oracle_bindings as ob
+    import parity
+    return ob, parity
 
 
 # ------------------------------------------------------------------------------------------------
@@ -102,111 +114,126 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-def make_copies(plan, want_bytes=2.5 * L2_BYTES, max_copies=12):
+def make_copies(plan, want_bytes=2.5 * L2_BYTES, max_copies=96):
     """Clones of the resident matrix so that a rotation over them defeats the L2."""
-    info = plan.info()
-    each = max(1, info["device_bytes"])
+    each = max(1, plan.info()["device_bytes"])
     n = int(min(max_copies, max(1, -(-want_bytes // each))))
     return [plan] + [plan.clone() for _ in range(n - 1)]
 
 
-GRAPH_STEPS = 100   # steps captured per CUDA graph
+GRAPH_STEPS = 100   # steps captured per CUDA graph at most
 GRAPH = True        # --no-graph clears it
+CHUNKS = 4          # the timed steps run as this many separately timed chunks (min / median)
 
 
-def timed_steps(torch, step, steps, warmup, stream, graph=True):
-    """Device time (ms) of exactly `steps` calls of step(i, cuda_stream) on `stream`, CUDA events,
-    device-wide synchronize on both sides.  With graph=True the steps are captured into CUDA
-    graphs (GRAPH_STEPS per graph, replayed back to back; a second graph for the remainder):
-    kernels launched one by one into a stream start on a ~2 us dispatch cadence on this driver,
-    a graph runs them back to back (tools/graph_vs_stream.py: 2.0-2.6 us per call)."""
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+def timed_steps(torch, step, steps, warmup, stream, graph=True, barrier=None):
+    """Device time of exactly `steps` calls of step(i, cuda_stream) on `stream`: CUDA events on that
+    stream, device-wide synchronize (and `barrier()`, across ranks) on both sides.  The steps run as
+    up to CHUNKS chunks, each between its own pair of events, so besides the total (first event to
+    last) there is a per-step time for every chunk: min / median.  With graph=True a chunk is a
+    CUDA graph replay (kernels launched one by one into a stream start on a ~2 us dispatch cadence
+    on this driver; a graph runs them back to back).  Chunks are an even number of steps (the
+    multi-GPU y buffers alternate).  Returns (total_ms, [us per step of every chunk])."""
+    n_chunks = max(1, min(CHUNKS, steps // 2))
+    per = steps // n_chunks
+    if per > 1 and per % 2:
+        per -= 1
+    per = max(1, min(per, GRAPH_STEPS if graph else per))
+    sizes = []
+    left = steps
+    while left > 0:
+        n = min(per, left)
+        sizes.append(n)
+        left -= n
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(sizes) + 1)]
     with torch.cuda.stream(stream):
         for i in range(warmup):
             step(i, stream.cuda_stream)
         stream.synchronize()
-        if not graph:
-            torch.cuda.synchronize()
-            e0.record(stream)
-            for i in range(steps):
-                step(i, stream.cuda_stream)
-            e1.record(stream)
+        graphs = {}
+        if graph:
+            for n in sorted(set(sizes)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    cs = torch.cuda.current_stream().cuda_stream
+                    for i in range(n):
+                        step(i, cs)
+                graphs[n] = g
+                g.replay()                                 # untimed: the first replay uploads the graph
             stream.synchronize()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1)
-        per = min(GRAPH_STEPS, steps)
-        reps, rem = divmod(steps, per)
-        graphs = []
-        for n in ([per] if rem == 0 else [per, rem]):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=stream):
-                cs = torch.cuda.current_stream().cuda_stream
+        torch.cuda.synchronize()
+        if barrier:
+            barrier()
+        ev[0].record(stream)
+        done = 0
+        for k, n in enumerate(sizes):
+            if graph:
+                graphs[n].replay()
+            else:
                 for i in range(n):
-                    step(i, cs)
-            graphs.append(g)
-        graphs[0].replay()                                 # untimed: first replay uploads the graph
-        if rem:
-            graphs[1].replay()
+                    step(done + i, stream.cuda_stream)
+            done += n
+            ev[k + 1].record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
-        e0.record(stream)
-        for _ in range(reps):
-            graphs[0].replay()
-        if rem:
-            graphs[1].replay()
-        e1.record(stream)
-        stream.synchronize()
-        torch.cuda.synchronize()
-    return e0.elapsed_time(e1)
+        if barrier:
+            barrier()
+    total = ev[0].elapsed_time(ev[-1])
+    per_step = [ev[k].elapsed_time(ev[k + 1]) * 1e3 / n for k, n in enumerate(sizes)]
+    return total, per_step
 
 
-def time_loop(torch, plans, dx, dy, steps, warmup, stream, graph=True):
-    """`steps` calls rotating over `plans` (clones of one matrix, > 2.5x L2 in total)."""
-    n = len(plans)
-    return timed_steps(torch, lambda i, cs: plans[i % n].run(dx, dy, cs), steps, warmup, stream, graph)
+def stats(per_step):
+    return {"min": round(min(per_step), 3), "median": round(statistics.median(per_step), 3), "chunks": len(per_step)}
 
 
-def measure_variant(torch, S, variant, build, x, steps, warmup, stream, check=None):
-    """Pack, clone, time.  Returns a dict; `build(variant)` returns a Plan."""
+def record_parity(what, fn):
+    """Runs a parity check; a failure is recorded (exit code != 0 at the end) instead of losing the line."""
+    try:
+        fn()
+        return "ok"
+    except AssertionError as e:
+        PARITY_FAILED.append(f"{what}: {e}")
+        return "FAILED: " + str(e)[:160]
+
+
+def measure_variant(torch, S, variant, build, x, steps, warmup, stream, check=None, hot=False):
+    """Pack, check against the oracle, clone, time.  `build(variant)` returns a Plan;
+    `check(variant, y)` raises AssertionError on a parity failure."""
     t0 = time.perf_counter()
     plan = build(variant)
     pack_s = time.perf_counter() - t0
     info = plan.info()
     alg, phys, nnz_t = plan.traffic(x)
-    plans = make_copies(plan)
     dx = torch.from_numpy(x).cuda()
     dy = torch.zeros(info["N"], dtype=torch.float32, device="cuda")
+    parity = None
     if check is not None:
         plan.run(dx, dy, stream.cuda_stream)
         stream.synchronize()
-        check(variant, dy.cpu().numpy())
-    ms = time_loop(torch, plans, dx, dy, steps, warmup, stream, graph=GRAPH)
+        y = dy.cpu().numpy()
+        parity = record_parity(f"{variant} {info['M']}x{info['N']}", lambda: check(variant, y))
+    plans = make_copies(plan)
+    n = len(plans)
+    ms, per = timed_steps(torch, lambda i, cs: plans[i % n].run(dx, dy, cs), steps, warmup, stream, graph=GRAPH)
     us = ms * 1e3 / steps
-    res = {"us_per_call": round(us, 3), "alg_MB": round(alg / 1e6, 3), "phys_MB": round(phys / 1e6, 3),
+    res = {"us_per_call": round(us, 3), "us_min": stats(per)["min"], "us_median": stats(per)["median"],
+           "alg_MB": round(alg / 1e6, 3), "phys_MB": round(phys / 1e6, 3),
            "eff_GBps": round(alg / (us * 1e-6) / 1e9, 1), "phys_GBps": round(phys / (us * 1e-6) / 1e9, 1),
-           "nnz_touched": nnz_t, "l2_copies": len(plans), "resident_MB": round(info["device_bytes"] / 1e6, 1),
+           "nnz_touched": nnz_t, "l2_copies": n, "resident_MB": round(info["device_bytes"] / 1e6, 1),
            "grid": [info["grid_x"], info["grid_y"]], "kernels_per_call": info["kernels_per_run"],
            "slab_cols": info["slab_cols"], "row_splits": info["row_splits"], "pack_s": round(pack_s, 2)}
+    if parity is not None:
+        res["parity"] = parity
+    if hot:                                               # the same call on ONE resident copy: L2-warm when it fits
+        ms_h, per_h = timed_steps(torch, lambda i, cs: plan.run(dx, dy, cs), steps, warmup, stream, graph=GRAPH)
+        res["hot_l2_us_per_call"] = round(ms_h * 1e3 / steps, 3)
     return res, plans, (dx, dy), (alg, phys)
-
-
-def e2e_loop(plan, x, N, steps, warmup, torch):
-    """The reference launcher's per-call part through the C-ABI with HOST buffers:
-    H2D x, kernels, D2H y, synchronise — every step (spmv_run_host)."""
-    hx = torch.from_numpy(x).pin_memory()
-    hy = torch.empty(N, dtype=torch.float32).pin_memory()
-    for _ in range(warmup):
-        plan.run_host_ptr(hx.data_ptr(), hy.data_ptr())
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        plan.run_host_ptr(hx.data_ptr(), hy.data_ptr())
-    dt = time.perf_counter() - t0
-    return dt / steps, hx.numel() * 4, hy.numel() * 4, hy.numpy().copy()
 
 
 # ------------------------------------------------------------------------------------------------
 def step_alg_bytes(A, x, names):
-    """Algorithmic bytes of one step = one call of each variant in `names`."""
+    """Algorithmic bytes of one call of each variant in `names`."""
     M, N = A.shape
     nnz = int(np.count_nonzero(A))
     act = x != 0
@@ -218,110 +245,177 @@ def step_alg_bytes(A, x, names):
     return sum(per[v] for v in names)
 
 
-def cpu_reference_sampled(A, x, alg_bytes, steps, warmup, calls_per_step=1, budget_s=100.0):
-    """The reference's own CPU path (SgemvCPU, tester.cpp:36-45) from oracle/_ref when it was
-    built, else the oracle's restatement of it.  The reference has one CPU implementation for
-    every variant, so a step of `calls_per_step` SGEMV calls is that many SgemvCPU calls.  Each
-    call runs on the first `rows` rows of the full-width matrix (row stride stays N, as in the
-    reference), `rows` chosen so the run fits the time budget; throughput is scaled by rows/M."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_bindings as ob
-    if ob.have_ref_cpu():
-        fn, kind = ob.ref_sgemv_cpu, "reference"
-    else:
-        fn, kind = ob.sgemv_dense, "port"
-    M, N = A.shape
-    probe_rows = 64
-    t0 = time.perf_counter()
-    fn(A[:probe_rows], x[:probe_rows])
-    per_row = (time.perf_counter() - t0) / probe_rows
-    rows = int(min(M, max(32, budget_s / max(1, (steps + warmup) * calls_per_step) / per_row)))
-    rows = max(32, rows // 32 * 32)
-    Ar, xr = np.ascontiguousarray(A[:rows]), np.ascontiguousarray(x[:rows])
-    for _ in range(warmup * calls_per_step):
-        fn(Ar, xr)
-    t0 = time.perf_counter()
-    for _ in range(steps * calls_per_step):
-        fn(Ar, xr)
-    dt = (time.perf_counter() - t0) / steps
-    frac = rows / M
-    gbps = alg_bytes * frac / dt / 1e9
-    what = "the reference SgemvCPU (tester.cpp:36-45, oracle/_ref)" if kind == "reference" else "the oracle port of SgemvCPU"
-    sample = (f"{steps} steps of {calls_per_step} call(s) of {what} on the first {rows} of {M} rows of the "
-              f"full-width {M}x{N} matrix (dense loop, 1 thread, {dt / calls_per_step * 1e3:.1f} ms per call; "
-              f"full-matrix call ~{dt / calls_per_step / frac * 1e3:.0f} ms)")
-    return gbps, dt, kind, sample, frac
+def c5_alg_bytes(nnz_touched_total):
+    N = C5_SLAB_N * C5_SLABS
+    return 8.0 * nnz_touched_total + 4.0 * (N + 1) + 4.0 * C5_M + 4.0 * N
+
+
+def c5_config():
+    """The same dict in the GPU arm and the reference arm (the driver compares them)."""
+    return {"workload": "BASELINE config 5 (strong scaling): A 65536x1048576 fp32, 99% sparse, built in sparse form as eight "
+                        "131072-column slabs (seeds 5000..5007), x 50% activation-sparse (seed 4321); awsp, row strips "
+                        "(chunk_mode 4); one step = y = x.A for the whole matrix, rank r owns slabs [8r/N, 8(r+1)/N), "
+                        "fused all-gather of Y + in-kernel arrival",
+            "M": C5_M, "N": C5_SLAB_N * C5_SLABS, "slabs": C5_SLABS, "weight_sparsity": 1.0 - C5_DENSITY,
+            "activation_sparsity": C5_SX, "variant": HEADLINE, "chunk_mode": C5_CHUNK_MODE,
+            "l2": "inputs larger than L2: a rank's resident slabs are 0.7 GB (N = 8) to 5.6 GB (N = 1) against 126 MB of L2, and "
+                  "every step streams all of them once; no rotation or flush needed",
+            "launch": "GPU arm: CUDA graphs of the steps, timed in chunks (see 'timing'); reference arm: host loop"}
+
+
+def c5_slab_csc(synth, g):
+    return synth.bernoulli_csc(C5_M, C5_SLAB_N, C5_DENSITY, seed=5000 + g)
+
+
+def c5_sample(col_ptr, row_idx, vals, g, n_cols=C5_CHECK_COLS):
+    """A seeded sample of a slab's columns as a small CSR(A^T) of its own (for the oracle)."""
+    rng = np.random.default_rng(900 + g)
+    cols = np.sort(rng.choice(C5_SLAB_N, size=n_cols, replace=False))
+    lens = (col_ptr[cols + 1] - col_ptr[cols]).astype(np.int64)
+    cp = np.zeros(n_cols + 1, np.int64)
+    np.cumsum(lens, out=cp[1:])
+    take = np.concatenate([np.arange(col_ptr[c], col_ptr[c + 1]) for c in cols]) if n_cols else np.zeros(0, np.int64)
+    return cols, cp, row_idx[take].copy(), vals[take].copy()
+
+
+def check_sampled(y_slab, sample, x, what):
+    """y of one slab against the oracle on its sampled columns (fp32 sequential + fp64, parity.py gate)."""
+    ob, parity = oracle_bindings()
+    cols, cp, ri, va = sample
+    y32 = ob.csc_gemv(cols.size, cp, ri, va, x)
+    xa = x.astype(np.float64)[ri] * va.astype(np.float64)
+    seg = np.repeat(np.arange(cols.size), np.diff(cp))
+    y64 = np.bincount(seg, weights=xa, minlength=cols.size)
+    s = np.bincount(seg, weights=np.abs(xa), minlength=cols.size)
+    parity.check_y(y_slab[cols], y32, y64, s, what)
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baselines(A, x, col_csc, alg_bytes, budget_s=6.0):
+    """BASELINE.md §5 beside the GPU number, same inputs: (i) the reference's dense SgemvCPU (tester.cpp:36-45,
+    from oracle/_ref when built, else the oracle's restatement), 1 thread, dense A only; (ii) the CSR(A^T)
+    restatement of csr_naive.cu:14-22 on 1 thread and on all host cores (OpenMP).  1 warm-up + best of
+    up to 5, bounded by `budget_s` per leg.  Returns a dict of GB/s of algorithmic bytes and ms per call."""
+    ob, _ = oracle_bindings()
+    cores = os.cpu_count() or 1
+    out = {"nproc": cores}
+
+    def best_of(fn):
+        fn()
+        best, t_all = None, time.perf_counter()
+        for _ in range(5):
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            if time.perf_counter() - t_all > budget_s:
+                break
+        return best
+    if A is not None:
+        M = A.shape[0]
+        rows = M if M * A.shape[1] <= 4096 * 4096 else max(32, (M // 8) // 32 * 32)   # bounded sample of the rows
+        Ar, xr = np.ascontiguousarray(A[:rows]), np.ascontiguousarray(x[:rows])
+        fn, kind = (ob.ref_sgemv_cpu, "reference") if ob.have_ref_cpu() else (ob.sgemv_dense, "port")
+        dt = best_of(lambda: fn(Ar, xr)) * (M / rows)
+        out["dense_1t"] = {"ms_per_call": round(dt * 1e3, 3), "GBps": round(alg_bytes / dt / 1e9, 4), "kind": kind,
+                           "sample": f"first {rows} of {M} rows, scaled"}
+    N, cp, ri, va = col_csc
+    for name, th in (("csr_1t", 1), ("csr_all_cores", cores)):
+        dt = best_of(lambda: ob.csc_gemv(N, cp, ri, va, x, threads=th))
+        out[name] = {"ms_per_call": round(dt * 1e3, 3), "GBps": round(alg_bytes / dt / 1e9, 4), "threads": th}
+    return out
 
 
 def run_reference_arm(args):
+    """The CPU arm on the headline workload (config 5).  The reference's own CPU path is the dense
+    single-thread SgemvCPU (tester.cpp:36-45), which cannot hold this matrix (256 GB dense); the
+    arm therefore times the reference's sparse algorithm — csr_naive.cu:14-22 restated for the CPU
+    in the oracle (CSR of A^T, sequential per output) — with OpenMP on all host cores, on a bounded
+    sample: ONE of the eight slabs per step (outputs are independent: time is linear in slabs).
+    The dense SgemvCPU on a 65536 x 1024 block of the same slab is reported beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from spmv_test_b200 import synth
-    if args.gpus > 1:
-        # this arm's N > 1 workload is the config-5 family; the reference's CPU path is the dense loop,
-        # and a slab cannot exist in dense form (34 GB), so the bounded sample is a dense block of
-        # the first 1024 columns of one slab (outputs are independent: time is linear in columns)
-        cols = 1024
-        cp, ri, va = synth.bernoulli_csc(C5_M, cols, C5_DENSITY, seed=5000)
-        A = np.zeros((C5_M, cols), np.float32)
-        A[ri, np.repeat(np.arange(cols), np.diff(cp))] = va
-        x = synth.gen_vector(C5_M, C5_SX, seed=4321)
-        alg = 8.0 * float(np.count_nonzero(A[x != 0.0])) + 4.0 * (cols + 1) + 4.0 * C5_M + 4.0 * cols
-        names = [HEADLINE]
-        cfg = workload_config("c5", HEADLINE, None)
-        cfg["N_total"] = args.gpus * C5_SLAB_N
-        note = (f"config-5 slab sampled as a dense {C5_M}x{cols} block of its first columns (the job is "
-                f"{args.gpus * C5_SLAB_N // cols} such blocks, processed one after the other on one thread); ")
-    else:
-        M, N, sa, sx = synth.CONFIGS["c2"]
-        A = synth.gen_matrix(M, N, sa)
-        x = synth.gen_vector(M, sx)
-        names = list(STEP_VARIANTS)
-        alg = step_alg_bytes(A, x, names)
-        cfg = workload_config("c2", "+".join(names), None)
-        note = ""
-    gbps, dt, kind, sample, frac = cpu_reference_sampled(A, x, alg, args.steps, args.warmup, calls_per_step=len(names))
+    ob, _ = oracle_bindings()
+    cores = os.cpu_count() or 1
+    cp, ri, va = c5_slab_csc(synth, 0)
+    x = synth.gen_vector(C5_M, C5_SX, seed=4321)
+    nnz_t = int(np.count_nonzero(x[ri] != 0))
+    alg_slab = c5_alg_bytes(nnz_t * C5_SLABS) / C5_SLABS
+    for _ in range(args.warmup):
+        ob.csc_gemv(C5_SLAB_N, cp, ri, va, x, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ob.csc_gemv(C5_SLAB_N, cp, ri, va, x, threads=cores)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)        # per slab
+    gbps = alg_slab / dt / 1e9
+    # the reference's dense loop on a dense block of the slab's first 1024 columns
+    cols = 1024
+    A = np.zeros((C5_M, cols), np.float32)
+    A[ri[: cp[cols]], np.repeat(np.arange(cols), np.diff(cp[: cols + 1]))] = va[: cp[cols]]
+    fn, kind = (ob.ref_sgemv_cpu, "reference") if ob.have_ref_cpu() else (ob.sgemv_dense, "port")
+    t0 = time.perf_counter()
+    fn(A, x)
+    dt_dense = time.perf_counter() - t0
+    alg_block = 8.0 * float(np.count_nonzero(A[x != 0.0])) + 4.0 * (cols + 1) + 4.0 * C5_M / (C5_SLAB_N / cols) + 4.0 * cols
+    sample = (f"{args.steps} steps, each ONE of the 8 slabs (65536x131072, {ri.size} non-zeros) through the oracle's CSR(A^T) "
+              f"restatement of csr_naive.cu:14-22 with OpenMP on {cores} host threads: {dt * 1e3:.1f} ms per slab "
+              f"(whole matrix ~{dt * C5_SLABS * 1e3:.0f} ms)")
     line = {"impl": "reference", "metric": METRIC, "value": round(gbps, 4), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 4),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": cfg,
-            "cpu_baseline": {"value": round(gbps, 4), "unit": UNIT, "cores": 1, "kind": kind, "sample": note + sample},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * C5_SLABS * 1e3, 4),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": c5_config(),
+            "cpu_baseline": {"value": round(gbps, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "dense_reference": {"kind": kind, "cores": 1, "GBps": round(alg_block / dt_dense / 1e9, 4),
+                                                 "sample": f"SgemvCPU (tester.cpp:36-45) on the dense 65536x{cols} block of the "
+                                                           f"slab's first columns: {dt_dense * 1e3:.0f} ms (the matrix is "
+                                                           f"{C5_SLAB_N * C5_SLABS // cols} such blocks)"}},
             "e2e": {"value": round(gbps, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(cfg, variant, l2):
-    if cfg == "c2":
-        return {"workload": "BASELINE config 2: A 4096x14336 fp32, 70% weight-sparse, x 50% activation-sparse; one step = "
-                            f"one SGEMV call of each variant in [{variant}] on the same A and x, seeds 1234/4321",
-                "M": 4096, "N": 14336, "weight_sparsity": 0.7, "activation_sparsity": 0.5, "variant": variant,
-                "l2": l2}
-    return {"workload": "BASELINE config 5 family (weak scaling): per GPU a 131072-column slab of A "
-                        "(65536 rows, 99% sparse, built in sparse form), x 50% activation-sparse, awsp (lane-owned "
-                        "blocks, chunk_mode 3) + all-gather of Y; 8 GPUs = 65536x1048576",
-            "M": C5_M, "N_per_gpu": C5_SLAB_N, "weight_sparsity": 0.99, "activation_sparsity": C5_SX,
-            "variant": variant, "l2": l2}
-
-
 # ------------------------------------------------------------------------------------------------
-# Config 5 (1 % dense, half of the activations non-zero) runs on the lane-owned block form of the awsp
-# format (chunk_mode 3: every stored non-zero is read, x is a multiplier, one pass per chunk); the
-# row-addressable multi-row form (chunk_mode 0) is reported beside it on one GPU.
-C5_CHUNK_MODE = 3
+def build_c5_rank(S, synth, slab_ids, chunk_mode):
+    """This rank's slabs: generate (a small pool of host threads), sample for the oracle, pack."""
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=min(4, max(1, len(slab_ids)))) as ex:
+        cscs = list(ex.map(lambda g: c5_slab_csc(synth, g), slab_ids))
+    gen_s = time.perf_counter() - t0
+    plans, samples, nnz = [], [], []
+    t0 = time.perf_counter()
+    for g, (cp, ri, va) in zip(slab_ids, cscs):
+        samples.append(c5_sample(cp, ri, va, g))
+        plans.append(S.Plan.from_csc(HEADLINE, C5_M, C5_SLAB_N, cp, ri, va, chunk_mode=chunk_mode))
+        nnz.append(int(ri.size))
+    cscs.clear()
+    return plans, samples, nnz, gen_s, time.perf_counter() - t0
 
 
-def slab_unit(torch, S, synth, rank, steps, warmup, stream, chunk_mode=C5_CHUNK_MODE):
-    """One GPU's config-5 slab: build, time the kernel alone.  Returns (res, plans, bufs, x)."""
-    col_ptr, row_idx, vals = synth.bernoulli_csc(C5_M, C5_SLAB_N, C5_DENSITY, seed=5000 + rank)
-    x = synth.gen_vector(C5_M, C5_SX, seed=4321)
-
-    def build(v):
-        return S.Plan.from_csc(v, C5_M, C5_SLAB_N, col_ptr, row_idx, vals, chunk_mode=chunk_mode)
-    res, plans, bufs, bytes_ = measure_variant(torch, S, HEADLINE, build, x, steps, warmup, stream)
-    res["chunk_mode"] = chunk_mode
-    return res, plans, bufs, x, bytes_
+def gpu_comparators(torch, A, x, y_ref, stream):
+    """The reference's own kernels recompiled for sm_100a (oracle/_ref/libspmv_ref_gpu.so: awsp_ref.cu:6-185,
+    wsp.cu:59-138, asp.cu:116-211, csr_naive.cu, cublas.cu:33) on the 4096x4096 harness shape, as the
+    reference's launchers run them (one cold launch each, their own TIME_KERNEL bracket), next to
+    cublasSgemv through torch.  Test infrastructure: built only where /root/reference exists."""
+    ob, _ = oracle_bindings()
+    out = {}
+    if not ob.have_ref_gpu():
+        return {"unavailable": "oracle/_ref/libspmv_ref_gpu.so was not built (no /root/reference at build time)"}
+    for name, ver in (("awsp_ref", 0), ("awsp", 2), ("wsp", 1), ("asp", 2), ("csr_naive", 0), ("csr_tiling", 0), ("cublas", 0)):
+        try:
+            best = None
+            for _ in range(3):
+                y, ms = ob.ref_gpu_gemv(name, A, x, version=ver)
+                best = ms if best is None else min(best, ms)
+            out[f"{name}_v{ver}"] = {"us_per_call": round(best * 1e3, 2), "max_abs_diff_vs_oracle": float(np.max(np.abs(y - y_ref)))}
+        except Exception as e:
+            out[name] = {"error": str(e)[:120]}
+    return out
 
 
 def main():
@@ -330,10 +424,11 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--quick", action="store_true", help="headline variant only (used under ncu)")
-    ap.add_argument("--no-aux", action="store_true", help="skip config 4 / config-5 slab / CPU baseline legs")
+    ap.add_argument("--quick", action="store_true", help="headline only (used under ncu)")
+    ap.add_argument("--no-aux", action="store_true", help="skip the CPU-baseline / comparator / batched legs")
     ap.add_argument("--no-graph", action="store_true", help="launch every call into the stream instead of replaying CUDA graphs")
-    ap.add_argument("--variant", default=None, help="headline variant override (for profiling one kernel)")
+    ap.add_argument("--chunk-mode", type=int, default=C5_CHUNK_MODE, help="config-5 form: 4 row strips, 3 lane-owned blocks, 0 multi-row")
+    ap.add_argument("--join", default="arrive", choices=["arrive", "nccl"], help="N > 1: in-kernel arrival (default) or NCCL all_gather")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 10 if args.steps is None else args.steps
@@ -342,8 +437,8 @@ def main():
         return
     global GRAPH
     GRAPH = not args.no_graph
-    args.steps = 2000 if args.steps is None else args.steps
-    args.warmup = 50 if args.warmup is None else max(3, args.warmup)
+    args.steps = 200 if args.steps is None else args.steps
+    args.warmup = 20 if args.warmup is None else max(3, args.warmup)
 
     import torch
     import spmv_test_b200 as S
@@ -359,234 +454,278 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > C5_SLABS:
+        raise SystemExit(f"bench.py: the config-5 matrix has {C5_SLABS} column slabs; run with at most {C5_SLABS} GPUs")
     stream = torch.cuda.Stream()
     peak, peak_src = peaks()
     sampler = ClockSampler(local)
     sampler.start()
     extra = {}
+    barrier = (lambda: dist.barrier()) if dist is not None else None
 
-    if world == 1:
-        # ---------------- single GPU: config 2, one step = wsp + asp + awsp -----------------------
-        M, N, sa, sx = synth.CONFIGS["c2"]
-        A = synth.gen_matrix(M, N, sa)
-        x = synth.gen_vector(M, sx)
-        names = [args.variant] if args.variant else list(STEP_VARIANTS)
-        variants, sets, algs, physs = {}, {}, {}, {}
-        for v in names:
-            res, plans, (dx, dy), (alg, phys) = measure_variant(
-                torch, S, v, lambda vv: S.Plan.from_dense(vv, A), x, args.steps, args.warmup, stream)
-            variants[v], sets[v], algs[v], physs[v] = res, plans, alg, phys
-        # the timed region: K steps, each one call of every variant the config names
-        def step(i, cs):
-            for v in names:
-                pl = sets[v]
-                pl[i % len(pl)].run(dx, dy, cs)
-        ms = timed_steps(torch, step, args.steps, args.warmup, stream, graph=not args.no_graph)
-        alg_step = sum(algs.values())
-        value = alg_step / (ms / args.steps * 1e-3) / 1e9
-        # end to end through the host-buffer C-ABI call (H2D x, kernels, D2H y, synchronise)
-        e2e_s, h2d, d2h = 0.0, 0, 0
-        for v in names:
-            plans = sets[v]
-            plans[0].run(dx, dy, stream.cuda_stream)
-            stream.synchronize()
-            y_dev = dy.cpu().numpy()
-            t, bi, bo, y_e2e = e2e_loop(plans[0], x, N, args.steps, args.warmup, torch)
-            assert y_e2e.tobytes() == y_dev.tobytes(), f"{v}: host-buffer path and device path disagree"
-            variants[v]["e2e_us_per_call"] = round(t * 1e6, 2)
-            e2e_s += t
-            h2d += bi
-            d2h += bo
-        launches = args.steps * sum(sets[v][0].info()["kernels_per_run"] for v in names)
-        l2 = ("rotation over resident copies of every packed matrix (" +
-              ", ".join(f"{v}: {len(sets[v])} x {variants[v]['resident_MB']} MB" for v in names) + "), each > 2.5x L2 in total")
-        dominant = max(names, key=lambda v: variants[v]["us_per_call"])
-        for v in names:
-            for p in sets[v][1:]:
-                p.close()
-        if not args.quick:
-            for v in [v for v in ("wsp", "asp", "awsp", "tcsr") if v not in names]:
-                r, pl, _, _ = measure_variant(torch, S, v, lambda vv: S.Plan.from_dense(vv, A), x,
-                                              args.steps, args.warmup, stream)
-                variants[v] = r
-                for p in pl:
-                    p.close()
-            cfgs = {}
-            for name in ("c1", "c3", "c0"):
-                Mc, Nc, sac, sxc = synth.CONFIGS[name]
-                Ac = synth.gen_matrix(Mc, Nc, sac)
-                xc = synth.gen_vector(Mc, sxc)
-                cfgs[name] = {"M": Mc, "N": Nc, "weight_sparsity": sac, "activation_sparsity": sxc}
-                for v in ("wsp", "asp", "awsp", "tcsr"):
-                    r, pl, _, _ = measure_variant(torch, S, v, lambda vv: S.Plan.from_dense(vv, Ac), xc,
-                                                  args.steps, args.warmup, stream)
-                    cfgs[name][v] = {k: r[k] for k in ("us_per_call", "alg_MB", "phys_MB", "eff_GBps", "phys_GBps")}
-                    for p in pl:
-                        p.close()
-            extra["configs"] = cfgs
-        if not args.quick and not args.no_aux:
-            # batched (multi-vector) wsp: A streamed once for 4 activation vectors
-            try:
-                bp = [S.Plan.from_dense("wsp", A)]
-                bp += [bp[0].clone() for _ in range(2)]
-                Xb = np.stack([synth.gen_vector(M, sx, seed=10 + b) for b in range(4)])
-                dXb = torch.from_numpy(Xb).cuda()
-                dYb = torch.zeros((4, N), device="cuda")
-                alg_b = sum(bp[0].traffic(Xb[b])[0] for b in range(4))
-                nb = max(50, args.steps // 10)
-                ms_b = timed_steps(torch, lambda i, cs: bp[i % 3].run_batch(dXb, dYb, cs), nb, 5, stream, graph=GRAPH)
-                us_b = ms_b * 1e3 / nb
-                extra["batched_wsp"] = {"batch": 4, "us_per_batched_call": round(us_b, 3), "us_per_vector": round(us_b / 4, 3),
-                                        "eff_GBps": round(alg_b / (us_b * 1e-6) / 1e9, 1),
-                                        "note": "A's bytes are read once per 4 vectors, so this exceeds the single-vector HBM roofline"}
-                for p in bp:
-                    p.close()
-            except Exception as e:
-                extra["batched_wsp"] = {"error": str(e)[:200]}
-            r, pl, _, _, _ = slab_unit(torch, S, synth, 0, max(50, args.steps // 10), 5, stream)
-            extra["weak_scaling_unit"] = dict(r, workload="one GPU's config-5 slab (65536x131072, 99% sparse, x 50%), kernel only, "
-                                                          "lane-owned blocks (chunk_mode 3)")
-            for p in pl:
-                p.close()
-            r, pl, _, _, _ = slab_unit(torch, S, synth, 0, max(50, args.steps // 10), 5, stream, chunk_mode=0)
-            extra["weak_scaling_unit_row_form"] = dict(r, workload="the same slab in the row-addressable multi-row form (chunk_mode 0)")
-            for p in pl:
-                p.close()
-            # config 4: power-law row lengths, 1M x 1M, wsp (32-bit row ids, x gathered through L2)
-            try:
-                cp, ri, va = synth.powerlaw_csc(1 << 20, 1 << 20, seed=42)
-                x4 = synth.gen_vector(1 << 20, 0.0, seed=7)
-                r, pl, _, _ = measure_variant(torch, S, "wsp", lambda vv: S.Plan.from_csc(vv, 1 << 20, 1 << 20, cp, ri, va),
-                                              x4, max(50, args.steps // 10), 5, stream)
-                extra["config4_powerlaw"] = dict(r, workload="1Mx1M power-law rows (Pareto alpha=2, ~16 nnz/row), wsp, dense x")
-                for p in pl:
-                    p.close()
-            except Exception as e:  # never lose the headline line to an auxiliary config
-                extra["config4_powerlaw"] = {"error": str(e)[:200]}
-            cpu_gbps, cpu_dt, kind, sample, _ = cpu_reference_sampled(A, x, alg_step, 2, 1, calls_per_step=len(names),
-                                                                      budget_s=20.0)
-            extra["cpu_baseline"] = {"value": round(cpu_gbps, 4), "unit": UNIT, "cores": 1, "kind": kind, "sample": sample}
-        extra["variants"] = variants
-        extra["step"] = names
-        cfg = workload_config("c2", "+".join(names), l2)
-        cfg["launch"] = ("CUDA graphs of %d steps replayed back to back" % min(GRAPH_STEPS, args.steps)) if GRAPH else "one stream launch per call"
-        roof_alg, roof_us, phys = algs[dominant], variants[dominant]["us_per_call"], physs[dominant]
-        roof_kernel = {"wsp": "wsp_ring_kernel<uint2>", "asp": "asp_kernel", "awsp": "panel_kernel<16,false,false,8>",
-                       "tcsr": "panel_kernel<16,true,false,8>"}[dominant]
-        e2e_val = alg_step / e2e_s / 1e9
-        scaling = "weak"
-        traffic = ncu_traffic(f"c2/{dominant}")
-    else:
-        # ---------------- multi GPU: config-5 slabs + all-gather ------------------------------
-        res, plans, (dx, dy), x, (alg, phys) = slab_unit(torch, S, synth, rank, max(20, args.steps // 10), 5, stream)
-        bounds = [g * C5_SLAB_N for g in range(world + 1)]
-        n = len(plans)
-        state = {"i": 0}
+    # ---------------- the headline: config 5, this rank's slabs ------------------------------------
+    slab_ids = list(range(rank * C5_SLABS // world, (rank + 1) * C5_SLABS // world))
+    plans, samples, nnz, gen_s, pack_s = build_c5_rank(S, synth, slab_ids, args.chunk_mode)
+    x = synth.gen_vector(C5_M, C5_SX, seed=4321)
+    dx = torch.from_numpy(x).cuda()
+    N_total = C5_SLAB_N * C5_SLABS
+    tr = [p.traffic(x) for p in plans]
+    alg_rank, phys_rank, touched_rank = sum(t[0] for t in tr), sum(t[1] for t in tr), sum(t[2] for t in tr)
 
-        def local_run(d_x, d_y):
-            plans[state["i"] % n].run(d_x, d_y, torch.cuda.current_stream().cuda_stream)
-            state["i"] += 1
-        class _Rot:                                       # the sharded runner sees a rotating plan
-            def run(self, d_x, d_y, stream=None):
-                local_run(d_x, d_y)
-
-            def run_scatter(self, d_x, ptrs, offset, mc=0, stream=None):
-                plans[state["i"] % n].run_scatter(d_x, ptrs, offset, mc, torch.cuda.current_stream().cuda_stream)
-                state["i"] += 1
-        rot = _Rot()
-
-        def timed_join(join):
-            sh = S.ShardedSgemv(bounds, rank, world, plan=rot, join=join)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(stream):
-                for _ in range(args.warmup):
-                    y_full = sh.run(dx)
-                stream.synchronize()
-                dist.barrier()
-                torch.cuda.synchronize()
-                e0.record(stream)
-                for _ in range(args.steps):
-                    y_full = sh.run(dx)
-                e1.record(stream)
-                stream.synchronize()
-                torch.cuda.synchronize()
-                dist.barrier()
-            return sh, y_full, e0.elapsed_time(e1)
-
-        sh_nccl, y_nccl, ms_nccl = timed_join("nccl")
+    # the shared block: two copies of the full y + arrival flags (symmetric memory when N > 1)
+    nbytes = S.Group.block_bytes(N_total)
+    join_used, hdl, mc = "single GPU: eight slabs into one y, no join", None, 0
+    if world > 1 and args.join == "arrive":
+        import torch.distributed._symmetric_memory as symm
+        block = symm.empty(nbytes // 4, dtype=torch.float32, device=torch.device("cuda", local))
+        block.zero_()
+        hdl = symm.rendezvous(block, dist.group.WORLD)
         try:
-            sh, y_full, ms_fused = timed_join("fused")
-            assert torch.equal(y_full, y_nccl), "fused epilogue and NCCL all-gather disagree"
-            join_used = "fused epilogue (%s stores into symmetric memory + barrier)" % ("multicast" if sh.multicast else "peer")
-        except Exception as e:                            # no symmetric memory on this box: NCCL join
-            sh, y_full, ms_fused = sh_nccl, y_nccl, None
-            join_used = "nccl all_gather (fused epilogue unavailable: %s)" % str(e)[:120]
-        ms_join = ms_fused if ms_fused is not None else ms_nccl
-        e_ms = torch.tensor([ms_join], dtype=torch.float64, device="cuda")
-        t = torch.tensor([ms_join, alg, phys], dtype=torch.float64, device="cuda")
+            mc = int(hdl.multicast_ptr or 0)
+        except Exception:
+            mc = 0
+        if os.environ.get("SPMV_NO_MULTICAST"):
+            mc = 0
+        join_used = "fused epilogue (%s stores into symmetric memory) + in-kernel arrival flags" % ("multicast" if mc else "peer")
+    else:
+        block = torch.zeros(nbytes // 4, dtype=torch.float32, device="cuda")
+    use_group = world == 1 or args.join == "arrive"
+    if use_group:
+        grp = S.Group(C5_M, N_total, rank if world > 1 else 0, world if world > 1 else 1, block.data_ptr())
+        if world > 1:
+            grp.connect_ptrs([int(q) for q in hdl.buffer_ptrs], mc)
+            torch.cuda.synchronize()
+            dist.barrier()
+        for g, p in zip(slab_ids, plans):
+            grp.add(p, g * C5_SLAB_N)
+
+        def y_view(ptr):
+            off = (ptr - block.data_ptr()) // 4
+            return block[off: off + N_total]
+
+        def step(i, cs):
+            grp.run(dx, cs)
+        step_y = lambda: y_view(grp.run(dx, stream.cuda_stream))       # noqa: E731
+    else:                                                 # N > 1 with the NCCL join: local slabs, then all_gather
+        y_local = torch.zeros(len(slab_ids) * C5_SLAB_N, dtype=torch.float32, device="cuda")
+        y_all = torch.zeros(N_total, dtype=torch.float32, device="cuda")
+        join_used = "nccl all_gather_into_tensor"
+
+        def step(i, cs):
+            for k, p in enumerate(plans):
+                p.run(dx, y_local[k * C5_SLAB_N:].data_ptr(), cs)
+            dist.all_gather_into_tensor(y_all, y_local)
+
+        def step_y():
+            with torch.cuda.stream(stream):
+                step(0, stream.cuda_stream)
+            return y_all
+
+    # ---- parity before timing: own slabs against the oracle, every rank's copy of every slab bit-identical ----
+    with torch.cuda.stream(stream):
+        y_dev = step_y()
+        stream.synchronize()
+        y_full = y_dev.cpu().numpy().copy()
+        y_dev2 = step_y()                                  # the other y buffer, and run-to-run reproducibility
+        stream.synchronize()
+        y_full2 = y_dev2.cpu().numpy().copy()
+    if use_group:
+        grp.status()
+    par = {}
+    for k, g in enumerate(slab_ids):
+        ys = y_full[g * C5_SLAB_N:(g + 1) * C5_SLAB_N]
+        par[f"slab{g}_vs_oracle"] = record_parity(f"config 5 slab {g}", lambda: check_sampled(ys, samples[k], x, f"config 5 slab {g}"))
+    par["two_calls_bit_identical"] = record_parity("reproducibility", lambda: (_ for _ in ()).throw(AssertionError("y differs between two calls"))
+                                                   if y_full.tobytes() != y_full2.tobytes() else None)
+    digs = [digest(y_full[g * C5_SLAB_N:(g + 1) * C5_SLAB_N]) for g in range(C5_SLABS)]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {"digs": digs, "par": par, "failed": list(PARITY_FAILED)})
+        owner = {g: r for r in range(world) for g in range(r * C5_SLABS // world, (r + 1) * C5_SLABS // world)}
+        bad = [f"slab {g}: rank {r} holds {gathered[r]['digs'][g]}, owner rank {owner[g]} computed {gathered[owner[g]]['digs'][g]}"
+               for g in range(C5_SLABS) for r in range(world) if gathered[r]["digs"][g] != gathered[owner[g]]["digs"][g]]
+        all_par = {}
+        for r in range(world):
+            all_par.update(gathered[r]["par"])
+            for f in gathered[r]["failed"]:
+                if f not in PARITY_FAILED:
+                    PARITY_FAILED.append(f)
+        all_par["gathered_y_identical_on_all_ranks"] = "ok" if not bad else "FAILED: " + "; ".join(bad[:3])
+        if bad:
+            PARITY_FAILED.extend(bad)
+        par = all_par
+    par["oracle"] = (f"oracle/spmv_oracle.c orc_csc_gemv (csr_naive.cu:14-22 semantics, fp32 sequential) + fp64, {C5_CHECK_COLS} seeded "
+                     "columns per slab, tests/parity.py gate (1e-5 * sum|x a| per element, 1e-5 * max|y|, abs 1e-3)")
+
+    # ---- the timed region: K steps ----------------------------------------------------------------
+    ms, per = timed_steps(torch, step, args.steps, args.warmup, stream, graph=GRAPH, barrier=barrier)
+    if use_group:
+        grp.status()
+    t = torch.tensor([ms, alg_rank, phys_rank, float(touched_rank)], dtype=torch.float64, device="cuda")
+    if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         ms = float(tmax[0])
-        alg_all = float(t[1])
-        value = alg_all / (ms / args.steps * 1e-3) / 1e9
-        # end to end: pinned host x -> device, local kernel, all-gather, full y -> pinned host
+    alg_all = c5_alg_bytes(float(t[3]))
+    us_step = ms * 1e3 / args.steps
+    value = alg_all / (us_step * 1e-6) / 1e9
+
+    # the kernel alone (no join), this rank's slabs: the roofline's launch duration
+    n_local = len(plans)
+    dy_scratch = torch.zeros(C5_SLAB_N, dtype=torch.float32, device="cuda")
+    k_steps = max(8, args.steps // 2)
+    ms_k, per_k = timed_steps(torch, lambda i, cs: plans[i % n_local].run(dx, dy_scratch, cs), k_steps * n_local, 4, stream, graph=GRAPH)
+    us_call = ms_k * 1e3 / (k_steps * n_local)
+
+    # ---- end to end: pinned host x -> device, the step, this rank's columns of y -> pinned host ----
+    e2e = None
+    if use_group:
         hx = torch.from_numpy(x).pin_memory()
-        hy = torch.empty(world * C5_SLAB_N, dtype=torch.float32).pin_memory()
-        e2e_steps = max(10, args.steps // 10)
-        with torch.cuda.stream(stream):
-            for it in range(3 + e2e_steps):
-                if it == 3:
-                    stream.synchronize()
-                    dist.barrier()
-                    t0 = time.perf_counter()
-                dx.copy_(hx, non_blocking=True)
-                y_full = sh.run(dx)
-                hy.copy_(y_full, non_blocking=True)
-                stream.synchronize()
-            e2e_s = (time.perf_counter() - t0) / e2e_steps
+        own0, own_n = slab_ids[0] * C5_SLAB_N, len(slab_ids) * C5_SLAB_N
+        hy = torch.empty(own_n, dtype=torch.float32).pin_memory()
+        e_steps = max(4, args.steps // 2)
+        e_steps += e_steps % 2
+        for it in range(2 + e_steps):
+            if it == 2:
+                torch.cuda.synchronize()
+                if barrier:
+                    barrier()
+                t0 = time.perf_counter()
+            grp.run_host(hx.data_ptr(), hy.data_ptr(), own0, own_n)
+        e2e_s = (time.perf_counter() - t0) / e_steps
+        e2e_ok = record_parity("e2e path", lambda: (_ for _ in ()).throw(AssertionError("host-buffer path and device path disagree"))
+                               if hy.numpy().tobytes() != y_full[own0: own0 + own_n].tobytes() else None)
         te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te[0])
-        e2e_val = alg_all / e2e_s / 1e9
-        h2d, d2h = hx.numel() * 4, hy.numel() * 4
-        launches = args.steps * plans[0].info()["kernels_per_run"]
-        l2 = (f"rotation over {len(plans)} resident copies of the slab ({res['resident_MB']} MB each): "
-              "inputs larger than L2")
-        cfg = workload_config("c5", HEADLINE, l2)
-        cfg["N_total"] = world * C5_SLAB_N
-        extra["variants"] = {HEADLINE + "_kernel_only_rank0": res}
-        extra["allgather_bytes_per_step"] = world * C5_SLAB_N * 4
-        tn = torch.tensor([ms_nccl], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
-        extra["join"] = {"used": join_used, "us_per_step_fused": None if ms_fused is None else round(ms / args.steps * 1e3, 3),
-                         "us_per_step_nccl": round(float(tn[0]) / args.steps * 1e3, 3),
-                         "us_kernel_only_rank0": res["us_per_call"]}
-        roof_alg, roof_us = alg, res["us_per_call"]
-        roof_kernel = "panel_kernel<16,false,false,4,true> (lane-owned blocks)"
-        scaling = "weak"
-        traffic = ncu_traffic(f"c5/{HEADLINE}")
+        e2e = {"value": round(alg_all / e2e_s / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": world * C5_M * 4,
+               "d2h_bytes_per_step": N_total * 4, "us_per_step": round(e2e_s * 1e6, 2),
+               "timer": "host perf_counter around spmv_mg_run_host (H2D x, the step, D2H of the rank's own columns of y, "
+                        "synchronise), max over ranks; byte counts are summed over the ranks",
+               "matches_device_path": e2e_ok}
+
+    launches = args.steps * sum(p.info()["kernels_per_run"] for p in plans) + (args.steps if world > 1 and use_group else 0)
+    info0 = plans[0].info()
+    cfg = c5_config()
+    if args.chunk_mode != C5_CHUNK_MODE:
+        cfg["chunk_mode"] = args.chunk_mode
+    extra["timing"] = {"resident": f"{len(plans)} slabs of {round(info0['device_bytes'] / 1e6, 1)} MB on this rank",
+                       "launch": ("CUDA graphs of up to %d steps, %d timed chunks" % (GRAPH_STEPS, len(per))) if GRAPH else "one stream launch per call"}
+    form = {4: "strips_kernel (+ strips_reduce_kernel)", 3: "panel_kernel<16,false,false,4,true> (lane-owned blocks)"}.get(args.chunk_mode, "panel_kernel (multi-row)")
+    alg_call, phys_call = alg_rank / n_local, phys_rank / n_local
+    join = {"used": join_used, "us_per_step": round(us_step, 3), "us_kernels_only_this_rank": round(us_call * n_local, 3),
+            "us_join_overhead": round(us_step - us_call * n_local, 3)}
+    extra["join"] = join
+    extra["parity"] = par
+    extra["build"] = {"slabs_this_rank": slab_ids, "generate_s": round(gen_s, 1), "pack_s": round(pack_s, 1), "nnz_this_rank": int(sum(nnz))}
+    extra["us_per_step_stats"] = stats(per)
+    extra["us_per_slab_call_stats"] = stats(per_k)
+    roof = {"bound": "hbm", "achieved": round(alg_call / (us_call * 1e-6) / 1e9, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(alg_call / (us_call * 1e-6) / 1e9 / peak, 4), "traffic": ncu_traffic(f"c5/{HEADLINE}/mode{args.chunk_mode}"),
+            "peak_source": peak_src, "kernel": form, "us_per_launch": round(us_call, 3),
+            "alg_bytes_per_launch": alg_call, "phys_bytes_per_launch": phys_call,
+            "phys_frac": round(phys_call / (us_call * 1e-6) / 1e9 / peak, 4),
+            "launch": "one slab call (65536x131072): the strips kernel and its reduce kernel, timed alone on this rank"}
+
+    # ---------------- N = 1 extras: every other config, per variant, each checked ------------------
+    if world == 1 and not args.quick:
+        for p in plans:
+            p.close()
+        plans.clear()
+        if use_group:
+            grp.close()
+        del block
+        torch.cuda.empty_cache()
+        ob, parity = oracle_bindings()
+        v_steps, v_warm = max(50, args.steps * 5), 10
+        cfgs = {}
+        for name in ("c2", "c1", "c3", "c0"):
+            Mc, Nc, sac, sxc = synth.CONFIGS[name]
+            Ac = synth.gen_matrix(Mc, Nc, sac)
+            xc = synth.gen_vector(Mc, sxc)
+            y32 = ob.sgemv_dense(Ac, xc)
+            y64, sabs = ob.sgemv_dense_f64(Ac, xc)
+            cfgs[name] = {"M": Mc, "N": Nc, "weight_sparsity": sac, "activation_sparsity": sxc,
+                          "oracle": "orc_sgemv_dense (tester.cpp:36-45 restated), all columns"}
+            for v in ("wsp", "asp", "awsp", "tcsr"):
+                r, pl, _, _ = measure_variant(torch, S, v, lambda vv: S.Plan.from_dense(vv, Ac), xc, v_steps, v_warm, stream,
+                                              check=lambda vv, y: parity.check_y(y, y32, y64, sabs, f"{name} {vv}"), hot=True)
+                keep = ("us_per_call", "us_min", "us_median", "hot_l2_us_per_call", "alg_MB", "phys_MB", "eff_GBps", "phys_GBps",
+                        "l2_copies", "parity", "kernels_per_call")
+                cfgs[name][v] = {k: r[k] for k in keep if k in r}
+                cfgs[name][v]["frac_alg"] = round(r["eff_GBps"] / peak, 4)
+                cfgs[name][v]["frac_phys"] = round(r["phys_GBps"] / peak, 4)
+                for p in pl:
+                    p.close()
+            if name == "c0" and not args.no_aux:
+                extra["gpu_comparator"] = dict(gpu_comparators(torch, Ac, xc, y32, stream),
+                                               shape="4096x4096, 50%/50% (test/main.cpp), the reference launchers' own cold-launch timing")
+            if name == "c2" and not args.no_aux:
+                cscp = ob.dense_to_csc(Ac)
+                extra["cpu_baseline_c2"] = cpu_baselines(Ac, xc, (Nc, *cscp), step_alg_bytes(Ac, xc, ["awsp"]))
+        # config 4: power-law row lengths, 1M x 1M, wsp (32-bit row ids, x gathered through L2)
+        try:
+            cp4, ri4, va4 = synth.powerlaw_csc(1 << 20, 1 << 20, seed=42)
+            x4 = synth.gen_vector(1 << 20, 0.0, seed=7)
+            rng = np.random.default_rng(404)
+            cols4 = np.sort(rng.choice(1 << 20, size=4096, replace=False))
+            lens = (cp4[cols4 + 1] - cp4[cols4]).astype(np.int64)
+            scp = np.zeros(cols4.size + 1, np.int64)
+            np.cumsum(lens, out=scp[1:])
+            take = np.concatenate([np.arange(cp4[c], cp4[c + 1]) for c in cols4])
+            sample4 = (cols4, scp, ri4[take].copy(), va4[take].copy())
+            r, pl, _, _ = measure_variant(torch, S, "wsp", lambda vv: S.Plan.from_csc(vv, 1 << 20, 1 << 20, cp4, ri4, va4), x4,
+                                          max(50, args.steps), 5, stream,
+                                          check=lambda vv, y: check_sampled(y, sample4, x4, "config 4 wsp"))
+            cfgs["c4"] = {"M": 1 << 20, "N": 1 << 20, "workload": "power-law row lengths (Pareto alpha=2, ~16 nnz/row), dense x",
+                          "oracle": "orc_csc_gemv on 4096 seeded columns", "wsp": dict(r, frac_alg=round(r["eff_GBps"] / peak, 4))}
+            for p in pl:
+                p.close()
+        except Exception as e:                            # never lose the headline line to an auxiliary config
+            cfgs["c4"] = {"error": str(e)[:200]}
+        extra["configs"] = cfgs
+
+    # ---------------- the CPU baseline beside the headline (rank 0, N = 1) -------------------------
+    if world == 1 and not args.quick and not args.no_aux:
+        cores = os.cpu_count() or 1
+        cp, ri, va = c5_slab_csc(synth, 0)
+        ob, _ = oracle_bindings()
+        alg_slab = alg_all / C5_SLABS
+        ob.csc_gemv(C5_SLAB_N, cp, ri, va, x, threads=cores)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            ob.csc_gemv(C5_SLAB_N, cp, ri, va, x, threads=cores)
+        dt_all = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        ob.csc_gemv(C5_SLAB_N, cp, ri, va, x, threads=1)
+        dt_1 = time.perf_counter() - t0
+        extra["cpu_baseline"] = {"value": round(alg_slab / dt_all / 1e9, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"one of the 8 slabs (65536x131072, {ri.size} non-zeros) through the oracle's CSR(A^T) restatement of "
+                                           f"csr_naive.cu:14-22, OpenMP on {cores} host threads, best-effort mean of {reps}: {dt_all * 1e3:.1f} ms per slab",
+                                 "csr_1t": {"GBps": round(alg_slab / dt_1 / 1e9, 4), "ms_per_slab": round(dt_1 * 1e3, 1)},
+                                 "csr_all_cores": {"GBps": round(alg_slab / dt_all / 1e9, 4), "ms_per_slab": round(dt_all * 1e3, 1), "threads": cores},
+                                 "nproc": cores}
 
     clocks = sampler.result()
     if rank == 0:
-        achieved = roof_alg / (roof_us * 1e-6) / 1e9
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 6), "higher_is_better": True,
-                "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-                "us_per_call": round(ms / args.steps * 1e3, 3),
-                "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                             "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                             "kernel": roof_kernel,
-                             "alg_bytes_per_launch": roof_alg,
-                             "phys_bytes_per_launch": phys, "phys_frac": round(phys / (roof_us * 1e-6) / 1e9 / peak, 4)},
-                "e2e": {"value": round(e2e_val, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "us_per_call": round(e2e_s * 1e6, 2),
-                        "timer": "host perf_counter around the synchronous host-buffer call, max over ranks"},
-                "gpu_launches": launches, "clocks": clocks}
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                "us_per_step": round(us_step, 3), "roofline": roof,
+                "e2e": e2e if e2e is not None else {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                                    "note": "the NCCL-join comparison run has no host-buffer path"},
+                "gpu_launches": launches, "clocks": clocks, "parity_ok": not PARITY_FAILED}
         line.update(extra)
         print(json.dumps(line), flush=True)
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
+    if PARITY_FAILED:
+        print("PARITY FAILED:\n  " + "\n  ".join(PARITY_FAILED[:10]), file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -112,6 +112,9 @@ SPMV_API int         spmv_abi_version(void);
 SPMV_API const char *spmv_last_error(void);
 /* Number of CUDA devices visible, or a negative status.  Never throws, never exits. */
 SPMV_API int         spmv_device_count(void);
+/* Plans and groups live on the calling thread's current CUDA device (the reference uses device 0
+ * of CUDA_VISIBLE_DEVICES throughout); this selects it for callers without the CUDA runtime headers. */
+SPMV_API int         spmv_set_device(int device);
 
 /* ---- plans ------------------------------------------------------------------------------- */
 /*
@@ -146,6 +149,9 @@ SPMV_API int spmv_plan_create_dense_device(int variant, int64_t M, int64_t N, co
  * (BASELINE configs 4 and 5).  Input is the reference CSRMatrix orientation
  * (matrix_csr.cpp:8-22: one list per OUTPUT column i, entries (row j, value) with
  * j ascending) but with 64-bit pointers and the N+1 sentinel the reference omits.
+ * Inside a column the rows must ascend STRICTLY and lie in [0, M): a repeated (row, column)
+ * entry, an unsorted list or an out-of-range row is rejected with SPMV_ERR_ARG (entries are
+ * never summed), so every variant sees the same matrix.
  * Supported for SPMV_WSP, SPMV_AWSP and SPMV_TCSR.
  */
 SPMV_API int spmv_plan_create_csc(int variant, int64_t M, int64_t N, const int64_t *col_ptr,

@@ -9,3 +9,4 @@ no CPU compute path: every call that produces y needs the CUDA library and a GPU
 from ._cabi import LIB_PATH, SpmvError, lib, VARIANTS, LAYOUTS  # noqa: F401
 from .plan import Plan, compact_x, pack_dump, ref_pack  # noqa: F401
 from .partition import column_bounds, ShardedSgemv  # noqa: F401
+from .group import Group, local_group, group_run_host  # noqa: F401

@@ -181,6 +181,14 @@ int launch_asp_batch(spmv_plan *p, const float *d_x, long long ldx, const YDst &
     return SPMV_ERR_UNSUPPORTED;
 }
 
+// Round 2 tried two re-decompositions, both measured slower or equal on a B200 and removed again
+// (profiles/r02_notes.md): (a) a flat (tile, row) sequence cut into 2-5 CTAs per SM with 16/32-deep
+// rings (config 2: 25.9-29.5 us against 23.7 here; config 0: 11.8-16.5 against 11.7) — more bytes in
+// flight through cp.async do not help; (b) one warp per (128-column subtile, row range), 8 rows in
+// flight as plain register loads, 32 warps per SM, a separate reduce kernel (config 2: 23.5 us;
+// config 0 / 3: 13.9 / 14.1 against 11.7 / 9.4): with ~50 active rows per warp the per-warp ramp and
+// the extra launch outweigh the cheaper loads.  A plain read of the same pattern reaches 18 us on
+// config 2 (tools/ubench/rowpattern.cu); the remaining gap is the x-dependent head and the tail.
 // grid = (ceil(N/512), row splits): about 1.6 CTAs per SM, all resident at once — every CTA pays a
 // fixed few microseconds (x compaction, first rows, split reduction), so more splits are slower —
 // with the rows per split rounded DOWN to a multiple of 32 (at least 64).  Measured with dependent

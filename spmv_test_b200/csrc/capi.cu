@@ -173,7 +173,8 @@ static int setup_strips(spmv_plan *p, HostStrips &h, const spmv_options_t *o)
         h.ent.resize(h.ent.size() - 32);
     }
     if (!rc) rc = configure_strips(p, h, o);
-    p->row_nnz.swap(h.row_nnz);
+    p->fmt_groups = (int64_t)h.ent.size() / kStripPad;
+    p->row_nnz.swap(h.row_nnz); p->row_groups.swap(h.row_groups);
     return rc;
 }
 
@@ -327,6 +328,19 @@ int spmv_plan_create_dense(int variant, int64_t M, int64_t N, const float *A, in
                 e = cudaMemcpy2D(staged, (size_t)N * 4, A, (size_t)lda * 4, (size_t)N * 4, (size_t)M, cudaMemcpyHostToDevice);
             if (e != cudaSuccess) rc = cuda_error(e, "staging the dense matrix");
             else rc = create_from_device(p, variant, staged, N, opts);
+            if (rc && (!opts || opts->pack_mode == 0)) {
+                // pack_mode auto: a device-packer failure (no room to stage, a temporary that does not fit,
+                // a shape the device packers do not take) falls back to the host packers, which give the same bytes
+                if (staged) { cudaFree(staged); staged = nullptr; }
+                cudaGetLastError();
+                spmv_plan_destroy(p);
+                p = nullptr;
+                spmv_options_t host_opts{};
+                if (opts) host_opts = *opts;
+                host_opts.struct_size = sizeof(spmv_options_t);
+                host_opts.pack_mode = 1;
+                return spmv_plan_create_dense(variant, M, N, A, lda, &host_opts, out);
+            }
         } else if (variant == SPMV_WSP) {
             HostWsp w;
             rc = pack_wsp_dense(M, N, A, lda, opts ? opts->index_bits : 0, w);
@@ -403,8 +417,9 @@ int spmv_plan_create_csc(int variant, int64_t M, int64_t N, const int64_t *col_p
     if (variant == SPMV_ASP) return set_error(SPMV_ERR_UNSUPPORTED, "asp needs a dense matrix");
     if (!col_ptr) return set_error(SPMV_ERR_ARG, "col_ptr is null");
     if (N > 0 && col_ptr[N] > col_ptr[0] && (!row_idx || !values)) return set_error(SPMV_ERR_ARG, "null row_idx/values");
-    for (int64_t i = 0; i < N; i++)
-        if (col_ptr[i + 1] < col_ptr[i]) return set_error(SPMV_ERR_ARG, "col_ptr is not monotone at %lld", (long long)i);
+    if (check_csc(M, N, col_ptr, row_idx))
+        return set_error(SPMV_ERR_ARG, "CSR(A^T) input: col_ptr must be monotone, the rows of a column in range and strictly "
+                                       "ascending (a repeated (row, column) entry is rejected, not summed)");
     spmv_plan *p = nullptr;
     int rc = plan_begin(variant, M, N, &p);
     if (rc) return rc;
@@ -484,8 +499,8 @@ int spmv_plan_save(const spmv_plan_t *p, const char *path)
     if (strips) {
         hs.M = p->M; hs.N = p->N; hs.nnz = p->nnz; hs.strip_cols = p->strips.strip_cols; hs.bands = p->strips.bands;
         rc = fetch(hs.soff, p->strips.soff, (size_t)hs.bands * p->M * kStripsPerBand + 1);
-        if (!rc) rc = fetch(hs.ent, p->strips.ent, (size_t)hs.nnz);
-        hs.row_nnz = p->row_nnz;
+        if (!rc) rc = fetch(hs.ent, p->strips.ent, (size_t)p->fmt_groups * kStripPad);
+        hs.row_nnz = p->row_nnz; hs.row_groups = p->row_groups;
     } else if (p->variant == SPMV_WSP) {
         w.M = p->M; w.N = p->N; w.nnz = p->nnz; w.groups = p->fmt_groups; w.index_bits = p->wsp.index_bits;
         w.panels = p->wsp.panels; w.panel_rows = p->wsp.panel_rows;
@@ -519,7 +534,7 @@ int spmv_plan_save(const spmv_plan_t *p, const char *path)
         fw.vec(dense);
     } else if (strips) {                                  // marked by a group count of -1
         fw.pod<int64_t>(-1); fw.pod<int32_t>(hs.strip_cols); fw.pod<int32_t>(hs.bands);
-        fw.vec(hs.soff); fw.vec(hs.ent); fw.vec(hs.row_nnz);
+        fw.vec(hs.soff); fw.vec(hs.ent); fw.vec(hs.row_nnz); fw.vec(hs.row_groups);
     } else {
         fw.pod<int64_t>(h.groups); fw.pod<int32_t>(h.slab_cols); fw.pod<int32_t>(h.index_bits); fw.pod<int32_t>(h.slabs);
         fw.pod<int32_t>(h.row_blocks); fw.pod<int32_t>(h.tiled ? 1 : 0); fw.pod<int32_t>(h.block_rows);
@@ -562,6 +577,10 @@ int spmv_plan_load(const char *path, const spmv_options_t *opts, spmv_plan_t **o
                               w.colptr.size() == (size_t)panels * N + 1 && w.vals.size() == (size_t)(w.groups + 1) * 4 &&
                               (ib == 16 ? w.idx16.size() : w.idx32.size()) == w.vals.size() && w.colptr.back() == (uint32_t)w.groups;
             if (!sane) return fail("corrupt wsp plan file");
+            // rows per panel must match the shape (the kernel sizes its x slice and pad index from it)
+            const bool panels_ok = panels == 1 ? w.panel_rows == M
+                                               : (w.panel_rows > 0 && (int64_t)panels * w.panel_rows >= M && (int64_t)(panels - 1) * w.panel_rows < M);
+            if (!panels_ok || (ib == 16 && w.panel_rows >= 65536)) return fail("corrupt wsp plan file (row panels)");
             for (size_t i = 0; i + 1 < w.colptr.size(); i++) {
                 if (w.colptr[i] > w.colptr[i + 1]) return fail("corrupt wsp plan file (offsets)");
                 w.max_col_groups = std::max<int64_t>(w.max_col_groups, (int64_t)w.colptr[i + 1] - w.colptr[i]);
@@ -598,22 +617,29 @@ int spmv_plan_load(const char *path, const spmv_options_t *opts, spmv_plan_t **o
                 int32_t sw = 0, bands = 0;
                 fr.pod(sw); fr.pod(bands);
                 hs.strip_cols = sw; hs.bands = bands;
-                fr.vec(hs.soff); fr.vec(hs.ent); fr.vec(hs.row_nnz);
+                fr.vec(hs.soff); fr.vec(hs.ent); fr.vec(hs.row_nnz); fr.vec(hs.row_groups);
                 uint64_t tail = 0; fr.pod(tail);
                 const bool sane = fr.ok && tail == kFileMagic && sw >= 32 && sw <= kMaxStripCols && sw % 32 == 0 && nnz >= 0 &&
                                   bands == (int32_t)std::max<int64_t>(1, (N + (int64_t)sw * kStripsPerBand - 1) / ((int64_t)sw * kStripsPerBand)) &&
-                                  hs.soff.size() == (size_t)bands * M * kStripsPerBand + 1 && hs.ent.size() == (size_t)nnz &&
-                                  hs.row_nnz.size() == (size_t)M && hs.soff.back() == (uint32_t)nnz && hs.soff.front() == 0u;
+                                  hs.soff.size() == (size_t)bands * M * kStripsPerBand + 1 && hs.ent.size() < (size_t)UINT32_MAX &&
+                                  hs.row_nnz.size() == (size_t)M && hs.row_groups.size() == (size_t)M &&
+                                  hs.soff.back() == (uint32_t)hs.ent.size() && hs.soff.front() == 0u;
                 if (!sane) return fail("corrupt strips plan file");
+                int64_t real = 0;
                 for (size_t i = 0; i + 1 < hs.soff.size(); i++) {
-                    if (hs.soff[i] > hs.soff[i + 1]) return fail("corrupt strips plan file (offsets)");
-                    // columns inside the strip, strictly ascending inside a segment (distinct accumulators)
+                    if (hs.soff[i] > hs.soff[i + 1] || hs.soff[i] % kStripPad) return fail("corrupt strips plan file (offsets)");
+                    // columns inside the strip (stored + 1), strictly ascending inside a segment (distinct
+                    // accumulators); all-zero pads only at the end of a segment
+                    bool pads = false;
                     for (uint32_t k = hs.soff[i]; k < hs.soff[i + 1]; k++) {
-                        const uint32_t c = (uint32_t)(hs.ent[k] >> 32);          // column + 1
-                        if (c == 0u || c > (uint32_t)sw || (k > hs.soff[i] && c <= (uint32_t)(hs.ent[k - 1] >> 32)))
+                        const uint32_t c = (uint32_t)(hs.ent[k] >> 32);
+                        if (c == 0u) { if ((uint32_t)hs.ent[k] != 0u) return fail("corrupt strips plan file (pads)"); pads = true; continue; }
+                        if (pads || c > (uint32_t)sw || (k > hs.soff[i] && c <= (uint32_t)(hs.ent[k - 1] >> 32)))
                             return fail("corrupt strips plan file (column ids)");
+                        real++;
                     }
                 }
+                if (real != nnz) return fail("corrupt strips plan file (entry count)");
                 fclose(f); f = nullptr;
                 rc = plan_begin(variant, M, N, &p);
                 if (!rc) rc = setup_strips(p, hs, opts);
@@ -646,6 +672,16 @@ int spmv_plan_load(const char *path, const spmv_options_t *opts, spmv_plan_t **o
             for (size_t i = 0; i + 1 < h.off.size(); i++)
                 if (h.off[i] > h.off[i + 1] || h.off[i + 1] > (uint32_t)h.groups) return fail("corrupt panel plan file (offsets)");
             if (ib == 16 && !lob) for (uint16_t v : h.idx16) if (v >= sc) return fail("corrupt panel plan file (column ids)");
+            if (h.tiled)                                   // in-tile offsets: monotone and inside the tile
+                for (int sl = 0; sl < slabs; sl++)
+                    for (int b = 0; b < rb; b++) {
+                        const size_t t = (size_t)sl * ((size_t)rb + 1) + b;
+                        const uint32_t span = h.off[t + 1] - h.off[t];
+                        const uint16_t *r = &h.rel[((size_t)sl * rb + b) * kTileRows];
+                        if (r[0] != 0) return fail("corrupt panel plan file (tile offsets)");
+                        for (int k = 0; k < kTileRows; k++)
+                            if (r[k] > span || (k > 0 && r[k] < r[k - 1])) return fail("corrupt panel plan file (tile offsets)");
+                    }
             if (lob) {                                     // row ids must stay inside the matrix (x is read at block*rows + id)
                 int cb = 0;
                 while ((32 << cb) < sc) cb++;
@@ -718,12 +754,12 @@ int spmv_plan_traffic(const spmv_plan_t *p, const float *x, double *alg_bytes, d
     } else if (p->strips.strip_cols > 0) {
         // row strips: 8 bytes per entry of an active row, one 64-byte offset record per (band, active row),
         // one partial band row per CTA written and read back
-        int64_t active = 0;
+        int64_t active = 0, stored = 0;
         for (int64_t j = 0; j < p->M; j++)
-            if (x[j] != 0.0f) { touched += p->row_nnz[j]; active++; }
+            if (x[j] != 0.0f) { touched += p->row_nnz[j]; stored += (int64_t)p->row_groups[j] * kStripPad; active++; }
         alg = 8.0 * touched + 4.0 * (N + 1) + vec;
         const double part_io = p->strips.ctas_per_band > 1 ? 2.0 * 4.0 * (double)p->grid.x * p->tile_width : 0.0;
-        phys = 8.0 * touched + (double)active * p->strips.bands * kStripsPerBand * 4.0 + 4.0 * M * p->strips.bands + 4.0 * N + part_io;   // every band's CTAs read x once
+        phys = 8.0 * stored + (double)active * p->strips.bands * kStripsPerBand * 4.0 + 4.0 * M * p->strips.bands + 4.0 * N + part_io;   // every band's CTAs read x once
     } else {
         int64_t groups = 0;
         for (int64_t j = 0; j < p->M; j++)

@@ -101,6 +101,8 @@ struct HostPanel {
 //     the entries are in ascending column order, so they are distinct accumulators; the all-zero
 //     entry (what a zero-filled copy produces for an idle lane) addresses accumulator 0, which no
 //     column uses;
+//   * a segment is padded with all-zero entries to a multiple of kStripPad = 4 entries, so it starts
+//     on a 32-byte sector boundary (a warp's load of ~20 entries then touches 6 sectors, not 7);
 //   * soff[(band*M + row)*16 + strip] = first entry of the segment (32-bit; one sentinel at the end).
 // The kernel (strips.cu) gives a band's row range to a 16-warp CTA, warp w owns strip w: one
 // row segment = one 32-lane window, one entry per lane, no two lanes on one accumulator, so a
@@ -108,6 +110,7 @@ struct HostPanel {
 // ------------------------------------------------------------------------------------------
 constexpr int kStripsPerBand = 16;
 constexpr int kMaxStripCols = 2112;      // 16 x (strip accumulators + ring + row table) must fit 227 KB
+constexpr int kStripPad = 4;             // entries per padding unit (32 bytes)
 constexpr double kStripTargetNnz = 20.5; // mean non-zeros per (row, strip): P(> 32) stays under 1 %
 
 struct HostStrips {
@@ -116,7 +119,8 @@ struct HostStrips {
     int bands = 0;
     std::vector<uint64_t> ent;       // value bits | (uint64)(column + 1) << 32
     std::vector<uint32_t> soff;      // bands*M*16 + 1
-    std::vector<int32_t> row_nnz;    // [M] stored nnz per row (all bands) — traffic accounting
+    std::vector<int32_t> row_nnz;    // [M] non-zeros per row (all bands)              — traffic accounting
+    std::vector<int32_t> row_groups; // [M] stored entries per row / kStripPad (pads included)
 };
 
 } // namespace spmv

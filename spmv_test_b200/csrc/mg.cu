@@ -242,6 +242,14 @@ int spmv_mg_run_host(spmv_mg_t *g, const float *x, float *y, int64_t y_begin, in
 
 } // extern "C"
 
+// plans and groups are created on the calling thread's current device; a host program without the
+// CUDA runtime headers (the drop-in launchers) selects it through this
+extern "C" int spmv_set_device(int device)
+{
+    SPMV_CUDA(cudaSetDevice(device));
+    return SPMV_OK;
+}
+
 // ---- several devices of ONE process (the reference's harness is a single process) -----------------
 // Every device gets its own group handle (rank = position in `devices`); the blocks are plain
 // cudaMalloc memory made mutually accessible with peer access, so the epilogues' stores to a

@@ -17,6 +17,22 @@
 
 namespace spmv {
 
+// CSR(A^T) input rule (spmv_b200.h): inside a column the rows ascend STRICTLY — a repeated (row,
+// column) pair would make two entries of one segment share an accumulator in the panel and strip
+// kernels (lost update) while wsp would add them, so the variants would disagree; out-of-range rows
+// and unsorted lists are rejected the same way.
+int check_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx)
+{
+    for (int64_t i = 0; i < N; i++) {
+        if (col_ptr[i + 1] < col_ptr[i]) return SPMV_ERR_ARG;
+        for (int64_t k = col_ptr[i]; k < col_ptr[i + 1]; k++) {
+            if (row_idx[k] < 0 || row_idx[k] >= M) return SPMV_ERR_ARG;
+            if (k > col_ptr[i] && row_idx[k] <= row_idx[k - 1]) return SPMV_ERR_ARG;
+        }
+    }
+    return SPMV_OK;
+}
+
 // ---------------------------------------------------------------------------- WSP ---------
 // Lists are indexed by l = panel * N + column.
 static void wsp_finish_layout(HostWsp &w, const std::vector<int64_t> &list_nnz)
@@ -516,6 +532,8 @@ void strips_begin(int64_t M, int64_t N, int strip_cols, HostStrips &h)
     h.bands = (int)std::max<int64_t>(1, (N + band_cols - 1) / band_cols);
     h.soff.assign((size_t)h.bands * M * kStripsPerBand + 1, 0u);
     h.row_nnz.assign((size_t)M, 0);
+    h.row_groups.assign((size_t)M, 0);
+    h.nnz = 0;
 }
 inline uint64_t strip_entry(float v, uint32_t col)       // column inside the strip, stored + 1 (formats.hpp)
 {
@@ -549,12 +567,13 @@ int pack_strips_dense(int64_t M, int64_t N, const float *A, int64_t lda, int str
                 const int64_t c0 = b * band_cols + (int64_t)s * strip_cols;
                 const int64_t c1 = std::min<int64_t>(N, c0 + strip_cols);
                 for (int64_t c = c0; c < c1; c++)
-                    if (row[c] != 0.0f) { h.ent.push_back(strip_entry(row[c], (uint32_t)(c - c0))); h.row_nnz[(size_t)j]++; }
+                    if (row[c] != 0.0f) { h.ent.push_back(strip_entry(row[c], (uint32_t)(c - c0))); h.row_nnz[(size_t)j]++; h.nnz++; }
+                while (h.ent.size() % kStripPad) h.ent.push_back(0);       // all-zero pads: 32-byte segments
+                h.row_groups[(size_t)j] += (int32_t)((h.ent.size() - h.soff[seg]) / kStripPad);
             }
         }
     if (h.ent.size() >= (size_t)UINT32_MAX) return SPMV_ERR_UNSUPPORTED;
     h.soff[seg] = (uint32_t)h.ent.size();
-    h.nnz = (int64_t)h.ent.size();
     return SPMV_OK;
 }
 
@@ -574,36 +593,52 @@ int pack_strips_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t 
     if (strip_cols < 32 || strip_cols > kMaxStripCols || strip_cols % 32) return SPMV_ERR_ARG;
     strips_begin(M, N, strip_cols, h);
     h.nnz = nnz;
-    h.ent.assign((size_t)nnz, 0);
     const int64_t band_cols = (int64_t)strip_cols * kStripsPerBand;
     const size_t per_band = (size_t)M * kStripsPerBand;
-    // entries per band -> the band's first entry
-    std::vector<int64_t> band_first((size_t)h.bands + 1, 0);
-    for (int b = 0; b < h.bands; b++) {
-        int64_t n = 0;
-        const int64_t c1 = std::min<int64_t>(N, (b + 1) * band_cols);
-        for (int64_t c = b * band_cols; c < c1; c++)
-            for (int64_t k = col_ptr[c]; k < col_ptr[c + 1]; k++) n += (values[k] != 0.0f);
-        band_first[(size_t)b + 1] = band_first[(size_t)b] + n;
-    }
     const int n_threads = pack_threads(h.bands);
-    std::vector<std::vector<int32_t>> rn((size_t)n_threads);
-    int dup_rc = SPMV_OK;
-    auto worker = [&](int t) {
-        std::vector<int32_t> &row_cnt = rn[(size_t)t];
-        row_cnt.assign((size_t)M, 0);
-        std::vector<uint32_t> cur(per_band);
+    auto run_pool = [&](auto &&fn) {
+        if (n_threads == 1) { fn(0); return; }
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_threads; t++) pool.emplace_back(fn, t);
+        for (std::thread &th : pool) th.join();
+    };
+    // pass 1: entries per segment (kept in soff for now), stored (padded) entries per band
+    std::vector<int64_t> band_first((size_t)h.bands + 1, 0);
+    run_pool([&](int t) {
         for (int b = t; b < h.bands; b += n_threads) {
             uint32_t *so = h.soff.data() + (size_t)b * per_band;
-            std::fill(cur.begin(), cur.end(), 0u);
             const int64_t cb = b * band_cols, c1 = std::min<int64_t>(N, cb + band_cols);
             for (int64_t c = cb; c < c1; c++) {
                 const int s = (int)((c - cb) / strip_cols);
                 for (int64_t k = col_ptr[c]; k < col_ptr[c + 1]; k++)
-                    if (values[k] != 0.0f) cur[(size_t)row_idx[k] * kStripsPerBand + s]++;
+                    if (values[k] != 0.0f) so[(size_t)row_idx[k] * kStripsPerBand + s]++;
             }
+            int64_t stored = 0;
+            for (size_t i = 0; i < per_band; i++) stored += (so[i] + kStripPad - 1) / kStripPad * kStripPad;
+            band_first[(size_t)b + 1] = stored;
+        }
+    });
+    for (int b = 0; b < h.bands; b++) band_first[(size_t)b + 1] += band_first[(size_t)b];
+    const int64_t stored_total = band_first[(size_t)h.bands];
+    if (stored_total >= (int64_t)UINT32_MAX) return SPMV_ERR_UNSUPPORTED;
+    h.ent.assign((size_t)stored_total, 0);                 // pads stay all-zero
+    // pass 2: offsets, then the entries (ascending column inside a segment)
+    std::vector<std::vector<int32_t>> rn((size_t)n_threads), rg((size_t)n_threads);
+    int dup_rc = SPMV_OK;
+    run_pool([&](int t) {
+        std::vector<int32_t> &row_cnt = rn[(size_t)t], &row_grp = rg[(size_t)t];
+        row_cnt.assign((size_t)M, 0); row_grp.assign((size_t)M, 0);
+        std::vector<uint32_t> cur(per_band);
+        for (int b = t; b < h.bands; b += n_threads) {
+            uint32_t *so = h.soff.data() + (size_t)b * per_band;
             uint32_t run = (uint32_t)band_first[(size_t)b];
-            for (size_t i = 0; i < per_band; i++) { const uint32_t n = cur[i]; so[i] = run; cur[i] = run; run += n; }
+            for (size_t i = 0; i < per_band; i++) {
+                const uint32_t n = so[i], padded = (n + kStripPad - 1) / kStripPad * kStripPad;
+                row_cnt[i / kStripsPerBand] += (int32_t)n;
+                row_grp[i / kStripsPerBand] += (int32_t)(padded / kStripPad);
+                so[i] = run; cur[i] = run; run += padded;
+            }
+            const int64_t cb = b * band_cols, c1 = std::min<int64_t>(N, cb + band_cols);
             for (int64_t c = cb; c < c1; c++) {
                 const int s = (int)((c - cb) / strip_cols);
                 const uint32_t lc = (uint32_t)(c - cb - (int64_t)s * strip_cols);
@@ -614,21 +649,14 @@ int pack_strips_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t 
                         // a repeated (row, column) pair would put two entries of one window on one accumulator
                         if (p > so[seg] && (uint32_t)(h.ent[p - 1] >> 32) == lc + 1u) dup_rc = SPMV_ERR_ARG;
                         h.ent[p] = strip_entry(values[k], lc);
-                        row_cnt[(size_t)row_idx[k]]++;
                     }
             }
         }
-    };
-    if (n_threads == 1) worker(0);
-    else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < n_threads; t++) pool.emplace_back(worker, t);
-        for (std::thread &th : pool) th.join();
-    }
+    });
     if (dup_rc) return dup_rc;
-    h.soff.back() = (uint32_t)nnz;
-    for (const std::vector<int32_t> &v : rn)
-        for (int64_t r = 0; r < M; r++) h.row_nnz[(size_t)r] += v[(size_t)r];
+    h.soff.back() = (uint32_t)stored_total;
+    for (int t = 0; t < n_threads; t++)
+        for (int64_t r = 0; r < M; r++) { h.row_nnz[(size_t)r] += rn[(size_t)t][(size_t)r]; h.row_groups[(size_t)r] += rg[(size_t)t][(size_t)r]; }
     return SPMV_OK;
 }
 
@@ -875,7 +903,7 @@ void dump_strips(const spmv::HostStrips &h, spmv_packed_dump_t *o)
     for (size_t k = 0; k < h.ent.size(); k++) {
         const uint32_t bits = (uint32_t)h.ent[k];
         std::memcpy(&v[k], &bits, 4);
-        c[k] = (uint32_t)(h.ent[k] >> 32) - 1u;               // the dump shows plain column numbers
+        c[k] = (uint32_t)(h.ent[k] >> 32) - 1u;               // the dump shows plain column numbers (pads: 0xffffffff)
     }
     o->vals = dup_vec(v); o->n_vals = (int64_t)v.size();
     o->idx = dup_vec(c); o->idx_bytes = (int64_t)c.size() * 4;
@@ -926,6 +954,8 @@ extern "C" int spmv_pack_dump_csc(int variant, int64_t M, int64_t N, const int64
     int rc = dump_common_check(variant, M, N, out);
     if (rc) return rc;
     if (!col_ptr) return spmv::set_error(SPMV_ERR_ARG, "col_ptr is null");
+    if (spmv::check_csc(M, N, col_ptr, row_idx))
+        return spmv::set_error(SPMV_ERR_ARG, "CSR(A^T) input: rows of a column must be in range and strictly ascending (no repeated entries)");
     try {
         if (variant == SPMV_WSP) {
             spmv::HostWsp w;

@@ -537,6 +537,10 @@ int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o)
     if (o && o->row_splits > 0) G = (int64_t)slabs * o->row_splits;       // forced: row_splits CTAs per slab
     const int64_t T = (int64_t)slabs * M;
     G = std::max<int64_t>(1, std::min<int64_t>(G, lob ? T : (T + 31) / 32));   // at least 32 rows (one block) per CTA
+    // the final sum stages one row offset per piece of a slab behind blockDim float4 of scratch: keep
+    // the pieces per slab inside the CTA's shared memory (forced options can ask for thousands)
+    const int64_t max_pieces = std::max<int64_t>(1, ((int64_t)p->smem - (int64_t)p->block * 16) / 4 - 2);
+    if ((G + slabs - 1) / slabs + 1 > max_pieces) G = std::max<int64_t>(1, (max_pieces - 1) * slabs);
     const int64_t max_range = (T + G - 1) / G;
     d.kmax = (int)(2 + max_range / M);
     p->row_splits = (int)((G + slabs - 1) / slabs);                        // reported: CTAs per slab (rounded up)

@@ -54,6 +54,7 @@ int pack_panel_dense(int64_t M, int64_t N, const float *A, int64_t lda, bool til
 int pack_panel_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx,
                    const float *values, bool tiled, int slab_cols, HostPanel &P, bool lane_owned = false);
 int choose_slab_cols(int64_t M, int64_t N, int64_t nnz);
+int check_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx);   // SPMV_OK or SPMV_ERR_ARG
 int pack_strips_dense(int64_t M, int64_t N, const float *A, int64_t lda, int strip_cols, HostStrips &h);
 int pack_strips_csc(int64_t M, int64_t N, const int64_t *col_ptr, const int32_t *row_idx, const float *values,
                     int strip_cols, HostStrips &h);

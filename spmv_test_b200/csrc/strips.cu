@@ -31,7 +31,7 @@ namespace {
 constexpr int kStripWarps = kStripsPerBand;               // warp w <-> strip w of the band
 constexpr int kStripThreads = kStripWarps * 32;
 #ifndef SPMV_STRIP_STAGES
-#define SPMV_STRIP_STAGES 16
+#define SPMV_STRIP_STAGES 32
 #endif
 constexpr int kStripStages = SPMV_STRIP_STAGES;           // rows in flight per warp (divides 32)
 // Where the rows in flight wait: 1 = in registers (four groups of four 8-byte loads per lane), 0 = in
@@ -42,13 +42,17 @@ constexpr int kStripStages = SPMV_STRIP_STAGES;           // rows in flight per 
 #define SPMV_STRIP_REGS 1
 #endif
 constexpr bool kStripRegs = SPMV_STRIP_REGS != 0;
+#ifndef SPMV_STRIP_PREFETCH
+#define SPMV_STRIP_PREFETCH 0
+#endif
+constexpr bool kStripPrefetch = SPMV_STRIP_PREFETCH != 0;
 // (four rows share one cp.async commit group and one set of broadcast loads of their scalars)
 constexpr int kStripSub = 2048;                           // rows compacted per pass
 constexpr int kStripSpan = kStripSub / kStripWarps;       // rows a warp compacts: 128
 constexpr int kStripSteps = kStripSpan / 32;
 
 __host__ __device__ constexpr int strip_warp_bytes(int sw) { return (sw + 32) * 4 + (kStripRegs ? 0 : kStripStages * 32 * 8); }
-__host__ __device__ constexpr int strip_smem_bytes(int sw) { return kStripWarps * (strip_warp_bytes(sw) + 64 * 12) + kStripSub * (2 + 4); }
+__host__ __device__ constexpr int strip_smem_bytes(int sw) { return kStripWarps * (strip_warp_bytes(sw) + 128 * 12) + kStripSub * (2 + 4); }
 
 // The row loop's ring traffic as volatile asm WITHOUT a memory clobber: volatile statements keep
 // their program order among themselves (ring read -> refill of the same slot -> commit -> wait ->
@@ -92,8 +96,8 @@ strips_kernel(const uint2 *__restrict__ ent, const uint32_t *__restrict__ soff, 
     uint2 *ring = reinterpret_cast<uint2 *>(wbase + (size_t)(sw + 32) * 4);
     uint16_t *rows_s = reinterpret_cast<uint16_t *>(smem_raw + (size_t)kStripWarps * strip_warp_bytes(sw));
     float *xs_s = reinterpret_cast<float *>(rows_s + kStripSub);
-    uint2 *tab_sl = reinterpret_cast<uint2 *>(xs_s + kStripSub) + warp * 64;           // (start, length) of two 32-row batches
-    float *tab_x = reinterpret_cast<float *>(reinterpret_cast<uint2 *>(xs_s + kStripSub) + kStripWarps * 64) + warp * 64;   // their x
+    uint2 *tab_sl = reinterpret_cast<uint2 *>(xs_s + kStripSub) + warp * 128;          // (start, length) of four 32-row batches
+    float *tab_x = reinterpret_cast<float *>(reinterpret_cast<uint2 *>(xs_s + kStripSub) + kStripWarps * 128) + warp * 128;   // their x
     const unsigned lt = (1u << lane) - 1u;
 
     for (int c = lane; c < sw + 32; c += 32) acc[c] = 0.0f;
@@ -200,27 +204,46 @@ strips_kernel(const uint2 *__restrict__ ent, const uint32_t *__restrict__ soff, 
                 __syncwarp();                             // the next row may hit the same columns from other lanes
             }
         };
-        uint2 *sl0 = tab_sl, *sl1 = tab_sl + 32;
-        float *xs0 = tab_x, *xs1 = tab_x + 32;
-        park(sl0, xs0, load_meta(0));
-        Meta ahead = load_meta(32);
+        // the table is a ring of four 32-row batches: batch i sits in slot i & 3; while batch i is being
+        // retired, batch i+1 is being loaded from and batch i+2 prefetched from
+        auto sl_of = [&](int bi) { return tab_sl + (bi & 3) * 32; };
+        auto xs_of = [&](int bi) { return tab_x + (bi & 3) * 32; };
+        // L2 prefetch of the rows 32 beyond the ones being loaded: one lane per 32-byte sector of the
+        // segment (segments start on sector boundaries).  No data returns to the SM, so it costs an
+        // issue slot but none of the data-pipe wavefronts the kernel is bound by, and the demand
+        // loads that follow find their sectors in L2.
+        auto prefetch_group = [&](const Four &f) {
+            if (!kStripPrefetch || (lane & 3)) return;
+            if (lane < (int)f.a.y) asm volatile("prefetch.global.L2 [%0];" ::"l"(ent_lane + (uint64_t)f.a.x * 8u));
+            if (lane < (int)f.a.w) asm volatile("prefetch.global.L2 [%0];" ::"l"(ent_lane + (uint64_t)f.a.z * 8u));
+            if (lane < (int)f.b.y) asm volatile("prefetch.global.L2 [%0];" ::"l"(ent_lane + (uint64_t)f.b.x * 8u));
+            if (lane < (int)f.b.w) asm volatile("prefetch.global.L2 [%0];" ::"l"(ent_lane + (uint64_t)f.b.z * 8u));
+        };
+        park(sl_of(0), xs_of(0), load_meta(0));
+        park(sl_of(1), xs_of(1), load_meta(32));
+        Meta ahead = load_meta(64);
         __syncwarp();
         constexpr int kGroups = kStripStages / 4;         // groups of four rows in flight
         uint2 E[kGroups][4];
 #pragma unroll
         for (int u = 0; u < kStripStages; u += 4) {
-            if (kStripRegs) load_group(group_meta(sl0, u), E[u / 4]);
-            else issue_group(group_meta(sl0, u), u);
+            const Four f = u < 32 ? group_meta(sl_of(0), u) : group_meta(sl_of(1), u - 32);
+            if (kStripRegs) load_group(f, E[u / 4]);
+            else issue_group(f, u);
         }
 #pragma unroll 1
-        for (int b0 = 0; b0 < total; b0 += 32) {
-            park(sl1, xs1, ahead);                        // batch b0 + 32 (its loads had a whole batch to land)
-            ahead = load_meta(b0 + 64);
+        for (int bi = 0; bi * 32 < total; bi++) {
+            park(sl_of(bi + 2), xs_of(bi + 2), ahead);    // (its loads had a whole batch to land)
+            ahead = load_meta((bi + 3) * 32);
             __syncwarp();
+            const uint2 *sl0 = sl_of(bi), *sl1 = sl_of(bi + 1), *sl2 = sl_of(bi + 2);
+            const float *xs0 = xs_of(bi);
 #pragma unroll
             for (int u = 0; u < 32; u += 4) {
                 // (the refill's scalars are read before the accumulator updates, not behind them)
-                const Four nx = u + kStripStages < 32 ? group_meta(sl0, u + kStripStages) : group_meta(sl1, u + kStripStages - 32);
+                constexpr int S = kStripStages;
+                const Four nx = u + S < 32 ? group_meta(sl0, u + S) : u + S < 64 ? group_meta(sl1, u + S - 32) : group_meta(sl2, u + S - 64);
+                if (kStripPrefetch) prefetch_group(u + S + 32 < 64 ? group_meta(sl1, u + S) : group_meta(sl2, u + S - 32));
                 if (kStripRegs) {
                     update_group(xs0, u, E[(u / 4) % kGroups]);
                     load_group(nx, E[(u / 4) % kGroups]);
@@ -246,8 +269,6 @@ strips_kernel(const uint2 *__restrict__ ent, const uint32_t *__restrict__ soff, 
                 }
                 __syncwarp();
             }
-            uint2 *t = sl0; sl0 = sl1; sl1 = t;
-            float *tx = xs0; xs0 = xs1; xs1 = tx;
         }
         if (!kStripRegs) ring_wait<0>();                  // (only empty groups are left)
     }

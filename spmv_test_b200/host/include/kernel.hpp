@@ -11,7 +11,8 @@
 // Mapping to the C-ABI variants (include/spmv_b200.h):
 //   wsp, csr_naive                 -> SPMV_WSP       asp, naive, tiling, cublas -> SPMV_ASP (dense A)
 //   awsp, awsp_ref, wsp_sm         -> SPMV_AWSP      csr_tiling                 -> SPMV_TCSR
-// cublas_gemv_gpu keeps its name for source compatibility; it no longer calls cuBLAS.
+// cublas_gemv_gpu is the reference's dense comparator: cublasSgemv (host/cublas_comparator.cpp), linked into
+// the harness only.  awsp_mg_gemv_gpu is an addition: the awsp launcher over every visible device.
 #pragma once
 #include <cstdio>
 #include <cstdlib>
@@ -27,6 +28,7 @@ void asp_gemv_gpu(int M, int N, float *A_host, float *X_host, float *Y_host, int
 void awsp_gemv_gpu(int M, int N, float *A_host, float *X_host, float *Y_host, int version);
 void awsp_ref_gemv_gpu(int M, int N, float *A_host, float *X_host, float *Y_host);
 void wsp_sm_gemv_gpu(int M, int N, float *A_host, float *X_host, float *Y_host);
+void awsp_mg_gemv_gpu(int M, int N, float *A_host, float *X_host, float *Y_host);   // not in the reference: all visible GPUs
 
 // The reference's helper macros, for translation units that include the CUDA runtime
 // themselves; this header does not need it.

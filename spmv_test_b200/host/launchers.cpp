@@ -3,6 +3,8 @@
 // A reference launcher is: pack A on the host, cudaMalloc, H2D, one timed launch, D2H,
 // cudaFree (e.g. awsp.cu:319-388).  Same life cycle here, one plan per call; callers that
 // want pack-once / run-many use the plan API of include/spmv_b200.h directly.
+#include <chrono>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -85,7 +87,42 @@ void tiling_gemv_gpu(int M, int N, float *A_host, float *X_host, float *Y_host)
     run_once("tiling_kernel", SPMV_ASP, M, N, A_host, X_host, Y_host);
 }
 
-void cublas_gemv_gpu(int M, int N, float *A, float *X, float *Y)
+// cublas_gemv_gpu (the reference's dense comparator, cublas.cu:4-44) lives in cublas_comparator.cpp:
+// it calls cublasSgemv like the reference does and is linked into the harness, not into the library.
+
+// Multi-GPU form of the awsp launcher (the reference is single-GPU): A's columns are
+// cut into one slab per visible device, every device packs and keeps its slab, one call runs all of
+// them (spmv_mg_group_run_host: peer stores into every device's y, in-kernel arrival) and Y comes
+// back whole.  With one device it is the plain launcher.
+void awsp_mg_gemv_gpu(int M, int N, float *A_host, float *X_host, float *Y_host)
 {
-    run_once("dense_sgemv", SPMV_ASP, M, N, A, X, Y);
+    int n_dev = spmv_device_count();
+    if (n_dev > 8) n_dev = 8;
+    while (n_dev > 1 && (N / 32) < n_dev) n_dev--;        // at least one 32-column unit per device
+    if (n_dev <= 1) { run_once("awsp_kernel (1 device)", SPMV_AWSP, M, N, A_host, X_host, Y_host); return; }
+    int devices[8];
+    int64_t bounds[9];
+    for (int d = 0; d < n_dev; d++) devices[d] = d;
+    if (spmv_partition_columns(N, n_dev, 32, nullptr, bounds) != SPMV_OK) die("awsp_mg partition");
+    spmv_mg_t *groups[8] = {};
+    spmv_plan_t *plans[8] = {};
+    if (spmv_mg_create_group(M, N, n_dev, devices, groups) != SPMV_OK) die("awsp_mg group");
+    for (int d = 0; d < n_dev; d++) {
+        if (spmv_set_device(devices[d]) != SPMV_OK) die("awsp_mg device");
+        const int64_t w = bounds[d + 1] - bounds[d];
+        if (spmv_plan_create_dense(SPMV_AWSP, M, w, A_host + bounds[d], N, nullptr, &plans[d]) != SPMV_OK) die("awsp_mg plan");
+        if (spmv_mg_add_plan(groups[d], plans[d], bounds[d]) != SPMV_OK) die("awsp_mg add");
+    }
+    if (spmv_mg_group_run_host(groups, n_dev, X_host, Y_host) != SPMV_OK) die("awsp_mg run");   // warm-up: module load on every device
+    const auto t0 = std::chrono::steady_clock::now();
+    if (spmv_mg_group_run_host(groups, n_dev, X_host, Y_host) != SPMV_OK) die("awsp_mg run");
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::cout << "awsp_kernel x " << n_dev << " devices (host x -> all devices, kernels, arrival, y slices -> host) took " << ms
+              << " ms" << std::endl;
+    for (int d = 0; d < n_dev; d++) {
+        spmv_set_device(devices[d]);
+        spmv_mg_destroy(groups[d]);
+        spmv_plan_destroy(plans[d]);
+    }
+    spmv_set_device(devices[0]);
 }

@@ -51,6 +51,8 @@ SparseSgemvTester::SparseSgemvTester(int m, int n) : m_(m), n_(n)
         // ... plus the csr launchers it declares (kernel.hpp:11-12) but never runs
         {"csr_naive", [](int M, int N, float *A, float *X, float *Y) { csr_naive_gemv_gpu(M, N, A, X, Y); }},
         {"csr_tiling", [](int M, int N, float *A, float *X, float *Y) { csr_tiling_gemv_gpu(M, N, A, X, Y); }},
+        // ... and the column-sharded form over every visible GPU (one device: the plain awsp launcher)
+        {"awsp multi-gpu", [](int M, int N, float *A, float *X, float *Y) { awsp_mg_gemv_gpu(M, N, A, X, Y); }},
     };
 }
 

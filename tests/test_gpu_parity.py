@@ -288,8 +288,9 @@ def test_traffic_accounting(S):
 
 def test_dropin_harness_binary(S):
     """build/sparse_sgemv = test/main.cpp + the drop-in tester over the C-ABI (reference
-    test/main.cpp:1-7, tester.cpp:15-34): ten launchers on 4096x4096, every output inside the
-    reference's own abs-1e-3 gate."""
+    test/main.cpp:1-7, tester.cpp:15-34): the reference's eight launchers (cublasSgemv comparator included), the
+    two csr launchers it declares but never runs, and the multi-GPU awsp launcher, on 4096x4096; every
+    output inside the reference's own abs-1e-3 gate."""
     import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -300,7 +301,8 @@ def test_dropin_harness_binary(S):
     out = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "========== OK ===========" in out.stdout
-    assert out.stdout.count(" took ") == 10 and out.stdout.count("start to launch") == 10
+    assert out.stdout.count(" took ") == 11 and out.stdout.count("start to launch") == 11
+    assert "cublasSgemv" in out.stdout, "the dense comparator is the library call the reference makes (cublas.cu:33)"
     assert out.stderr.strip() == ""
 
 

@@ -224,8 +224,10 @@ def _decode_strips(d):
     S16, sw, bands = d.row_blocks, d.slab_cols, d.slabs
     assert d.block_rows == -1 and S16 == 16 and d.index_bits == 32 and sw % 32 == 0
     assert bands == max(1, -(-d.N // (S16 * sw)))
-    assert d.off.size == bands * d.M * S16 + 1 and d.off[0] == 0 and d.off[-1] == d.vals.size == d.idx.size == d.nnz
-    assert np.all(np.diff(d.off.astype(np.int64)) >= 0)
+    assert d.off.size == bands * d.M * S16 + 1 and d.off[0] == 0 and d.off[-1] == d.vals.size == d.idx.size
+    assert np.all(np.diff(d.off.astype(np.int64)) >= 0) and np.all(d.off % 4 == 0), "segments start on 32-byte boundaries"
+    pad = d.idx == 0xFFFFFFFF
+    assert np.all(d.vals[pad] == 0) and int((~pad).sum()) == d.nnz
     A = np.zeros((d.M, bands * S16 * sw), np.float32)
     seg = 0
     for b in range(bands):
@@ -233,9 +235,11 @@ def _decode_strips(d):
             for s in range(S16):
                 e0, e1 = int(d.off[seg]), int(d.off[seg + 1])
                 seg += 1
-                c = d.idx[e0:e1].astype(np.int64)
+                real = ~pad[e0:e1]
+                assert e1 - e0 - int(real.sum()) < 4 and np.all(real[:int(real.sum())]), "fewer than 4 pads, all at the end"
+                c = d.idx[e0:e1][real].astype(np.int64)
                 assert np.all(c < sw) and np.all(np.diff(c) > 0), "columns of a segment ascend strictly"
-                A[row, (b * S16 + s) * sw + c] = d.vals[e0:e1]
+                A[row, (b * S16 + s) * sw + c] = d.vals[e0:e1][real]
     assert not np.any(A[:, d.N:])
     return A[:, :d.N]
 
@@ -271,7 +275,7 @@ def test_row_strips_width_rule_and_bad_input():
     d = S.pack_dump("awsp", csc=(cp, ri, va), shape=(4096, 32768), chunk_mode=4)
     assert d.slab_cols == 2048 and d.slabs == 1
     per_seg = np.diff(d.off.astype(np.int64))
-    assert 19.5 < per_seg.mean() < 21.5 and (per_seg > 32).mean() < 0.01
+    assert 19.5 < d.nnz / per_seg.size < 21.5 and (per_seg > 32).mean() < 0.01
     with pytest.raises(S.SpmvError):                      # strip width must be a multiple of 32 up to the shared-memory limit
         S.pack_dump("awsp", csc=(cp, ri, va), shape=(4096, 32768), chunk_mode=4, slab_cols=48)
     with pytest.raises(S.SpmvError):
@@ -280,3 +284,17 @@ def test_row_strips_width_rule_and_bad_input():
     cp2 = np.array([0, 2] + [2] * 31, np.int64)
     with pytest.raises(S.SpmvError):
         S.pack_dump("awsp", csc=(cp2, np.array([3, 3], np.int32), np.array([1.0, 2.0], np.float32)), shape=(8, 32), chunk_mode=4)
+
+
+@pytest.mark.parametrize("variant,opts", [("wsp", {}), ("awsp", {}), ("tcsr", {}), ("awsp", {"chunk_mode": 3, "slab_cols": 1024}),
+                                          ("awsp", {"chunk_mode": 4})])
+def test_csc_input_rule_repeated_or_unsorted_entries_are_rejected(variant, opts):
+    """a repeated (row, column) pair used to pack silently (awsp/tcsr lost an update, wsp summed)."""
+    import spmv_test_b200 as S
+    cp = np.array([0, 2] + [2] * 31, np.int64)
+    va = np.array([1.0, 2.0], np.float32)
+    for rows in ([0, 0], [5, 3], [1, 8]):                 # repeated, descending, out of range (M = 8)
+        with pytest.raises(S.SpmvError):
+            S.pack_dump(variant, csc=(cp, np.array(rows, np.int32), va), shape=(8, 32), **opts)
+    d = S.pack_dump(variant, csc=(cp, np.array([3, 5], np.int32), va), shape=(8, 32), **opts)
+    assert d.nnz == 2
