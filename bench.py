@@ -389,9 +389,15 @@ def build_c5_rank(S, synth, slab_ids, chunk_mode):
     gen_s = time.perf_counter() - t0
     plans, samples, nnz = [], [], []
     t0 = time.perf_counter()
+    import torch
     for g, (cp, ri, va) in zip(slab_ids, cscs):
         samples.append(c5_sample(cp, ri, va, g))
-        plans.append(S.Plan.from_csc(HEADLINE, C5_M, C5_SLAB_N, cp, ri, va, chunk_mode=chunk_mode))
+        if chunk_mode == 4:                               # row strips: packed by kernels from the CSR(A^T) arrays in HBM
+            d = [torch.from_numpy(a).cuda() for a in (cp, ri, va)]
+            plans.append(S.Plan.from_csc_device(HEADLINE, C5_M, C5_SLAB_N, *d, chunk_mode=chunk_mode))
+            del d
+        else:
+            plans.append(S.Plan.from_csc(HEADLINE, C5_M, C5_SLAB_N, cp, ri, va, chunk_mode=chunk_mode))
         nnz.append(int(ri.size))
     cscs.clear()
     return plans, samples, nnz, gen_s, time.perf_counter() - t0

@@ -14,7 +14,7 @@ LAYOUTS = {"csr": 0, "tcsr": 1, "wsp": 2, "asp": 3, "awsp": 4, "awsp_ref": 5}
 # every symbol include/spmv_b200.h declares (tests/test_cabi.py checks the header against this)
 SYMBOLS = [
     "spmv_abi_version", "spmv_last_error", "spmv_device_count", "spmv_set_device", "spmv_plan_create_dense", "spmv_plan_create_dense_device",
-    "spmv_plan_create_csc", "spmv_plan_info", "spmv_plan_destroy", "spmv_plan_clone", "spmv_plan_save", "spmv_plan_load",
+    "spmv_plan_create_csc", "spmv_plan_create_csc_device", "spmv_plan_info", "spmv_plan_destroy", "spmv_plan_clone", "spmv_plan_save", "spmv_plan_load",
     "spmv_plan_traffic", "spmv_run", "spmv_run_act", "spmv_run_batch", "spmv_run_scatter", "spmv_run_host", "spmv_compact_x",
     "spmv_compact_x_scratch_bytes", "spmv_partition_columns", "spmv_ref_pack",
     "spmv_ref_packed_free", "spmv_pack_dump_dense", "spmv_pack_dump_csc", "spmv_pack_dump_free",
@@ -83,6 +83,7 @@ def lib():
     L.spmv_plan_create_dense.argtypes = [i32, i64, i64, vp, i64, C.POINTER(Options), C.POINTER(vp)]
     L.spmv_plan_create_dense_device.argtypes = [i32, i64, i64, vp, i64, C.POINTER(Options), C.POINTER(vp)]
     L.spmv_plan_create_csc.argtypes = [i32, i64, i64, vp, vp, vp, C.POINTER(Options), C.POINTER(vp)]
+    L.spmv_plan_create_csc_device.argtypes = [i32, i64, i64, vp, vp, vp, C.POINTER(Options), C.POINTER(vp)]
     L.spmv_plan_info.argtypes = [vp, C.POINTER(PlanInfo)]
     L.spmv_plan_destroy.argtypes = [vp]
     L.spmv_plan_destroy.restype = None

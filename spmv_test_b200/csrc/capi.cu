@@ -450,6 +450,40 @@ int spmv_plan_create_csc(int variant, int64_t M, int64_t N, const int64_t *col_p
     return SPMV_OK;
 }
 
+int spmv_plan_create_csc_device(int variant, int64_t M, int64_t N, const int64_t *d_col_ptr, const int32_t *d_row_idx,
+                                const float *d_values, const spmv_options_t *opts, spmv_plan_t **out)
+{
+    if (!opts_ok(opts)) return set_error(SPMV_ERR_ARG, "bad spmv_options_t");
+    if (!want_strips(opts, variant))
+        return set_error(SPMV_ERR_UNSUPPORTED, "device-resident CSR(A^T) input is packed on the GPU for the row-strip form only "
+                                               "(SPMV_AWSP with chunk_mode 4); other forms take spmv_plan_create_csc");
+    if (!d_col_ptr) return set_error(SPMV_ERR_ARG, "d_col_ptr is null");
+    if (!d_row_idx || !d_values) {                        // legal only for a matrix without entries
+        int64_t ends[2] = {0, 0};
+        SPMV_CUDA(cudaMemcpy(&ends[0], d_col_ptr, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        SPMV_CUDA(cudaMemcpy(&ends[1], d_col_ptr + N, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        if (ends[1] != ends[0]) return set_error(SPMV_ERR_ARG, "null d_row_idx / d_values");
+    }
+    spmv_plan *p = nullptr;
+    int rc = plan_begin(variant, M, N, &p);
+    if (rc) return rc;
+    try {
+        HostStrips h;
+        rc = pack_strips_csc_device(p, d_col_ptr, d_row_idx, d_values, opts->slab_cols, h);
+        if (!rc) {
+            p->nnz = h.nnz;
+            rc = configure_strips(p, h, opts);
+            p->row_nnz.swap(h.row_nnz); p->row_groups.swap(h.row_groups);
+        }
+        if (!rc) rc = plan_finish(p);
+    } catch (const std::bad_alloc &) {
+        rc = set_error(SPMV_ERR_NOMEM, "out of host memory while packing");
+    }
+    if (rc) { spmv_plan_destroy(p); return rc; }
+    *out = p;
+    return SPMV_OK;
+}
+
 int spmv_plan_clone(const spmv_plan_t *src, spmv_plan_t **out)
 {
     if (!src || !out) return set_error(SPMV_ERR_ARG, "null argument");

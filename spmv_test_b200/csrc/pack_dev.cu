@@ -519,4 +519,157 @@ int pack_panel_device(spmv_plan *p, const float *d_A, int64_t lda, bool tiled, i
     return SPMV_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// row strips (formats.hpp: HostStrips) from CSR(A^T) ALREADY IN DEVICE MEMORY — the route for
+// matrices that never exist densely (BASELINE config 5).  check + count, per-segment counts
+// (integer atomics: the counts do not depend on their order), pad to 32 bytes, the shared scan,
+// then the fill: one CTA per (band, strip) walks the strip's columns IN ORDER, the threads of
+// the CTA share one column's entries — their rows are distinct, so no two threads touch the
+// same segment cursor — with a barrier between columns.  Entries of a segment therefore land in
+// ascending column order: the bytes are the host packer's (pack_strips_csc).
+// ------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256)
+strips_check_kernel(const int64_t *__restrict__ col_ptr, const int32_t *__restrict__ row_idx, const float *__restrict__ values,
+                    int M, long long N, unsigned long long *__restrict__ nnz, int *__restrict__ bad)
+{
+    __shared__ unsigned long long ws[8];
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    unsigned long long n = 0;
+    for (long long c = warp; c < N; c += n_warps) {
+        const long long a = col_ptr[c], b = col_ptr[c + 1];
+        if (b < a) { if (lane == 0) *bad = 1; continue; }
+        for (long long k = a + lane; k < b; k += 32) {
+            const int r = row_idx[k];
+            if (r < 0 || r >= M || (k > a && row_idx[k - 1] >= r)) *bad = 1;
+            n += values[k] != 0.0f;
+        }
+    }
+    n = block_sum_u64(n, ws);
+    if (threadIdx.x == 0 && n) atomicAdd(nnz, n);
+}
+
+__global__ void __launch_bounds__(256)
+strips_count_kernel(const int64_t *__restrict__ col_ptr, const int32_t *__restrict__ row_idx, const float *__restrict__ values,
+                    long long M, long long N, int sw, uint32_t *__restrict__ cnt)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long band_cols = (long long)sw * kStripsPerBand;
+    for (long long c = warp; c < N; c += n_warps) {
+        const long long band = c / band_cols;
+        const int strip = (int)((c - band * band_cols) / sw);
+        uint32_t *base = cnt + (size_t)band * M * kStripsPerBand + strip;
+        for (long long k = col_ptr[c] + lane; k < col_ptr[c + 1]; k += 32)
+            if (values[k] != 0.0f) atomicAdd(base + (size_t)row_idx[k] * kStripsPerBand, 1u);
+    }
+}
+
+// counts -> padded counts (in place); per-row statistics for the traffic accounting
+__global__ void __launch_bounds__(256)
+strips_pad_kernel(uint32_t *__restrict__ cnt, size_t segs, long long M, int *__restrict__ row_nnz, int *__restrict__ row_groups)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= segs) return;
+    const uint32_t n = cnt[i], padded = (n + kStripPad - 1) / kStripPad * kStripPad;
+    cnt[i] = padded;
+    if (n) {
+        const long long row = (long long)((i / kStripsPerBand) % (size_t)M);
+        atomicAdd(row_nnz + row, (int)n);
+        atomicAdd(row_groups + row, (int)(padded / kStripPad));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+strips_fill_kernel(const int64_t *__restrict__ col_ptr, const int32_t *__restrict__ row_idx, const float *__restrict__ values,
+                   long long M, long long N, int sw, uint32_t *__restrict__ cursor, uint2 *__restrict__ ent)
+{
+    const long long band = blockIdx.x / kStripsPerBand;
+    const int strip = blockIdx.x % kStripsPerBand;
+    const long long c0 = (band * kStripsPerBand + strip) * (long long)sw, c1 = min(N, c0 + sw);
+    uint32_t *cur = cursor + (size_t)band * M * kStripsPerBand + strip;
+    for (long long c = c0; c < c1; c++) {
+        const long long a = col_ptr[c], b = col_ptr[c + 1];
+        for (long long k = a + threadIdx.x; k < b; k += blockDim.x) {
+            const float v = values[k];
+            if (v != 0.0f) {
+                uint32_t *q = cur + (size_t)row_idx[k] * kStripsPerBand;   // rows of one column are distinct: no other thread is here
+                const uint32_t p = *q;
+                *q = p + 1u;
+                ent[p] = make_uint2(__float_as_uint(v), (uint32_t)(c - c0) + 1u);
+            }
+        }
+        __syncthreads();                                  // the next column may touch the same cursors
+    }
+}
+
+} // namespace
+
+int pack_strips_csc_device(spmv_plan *p, const int64_t *d_col_ptr, const int32_t *d_row_idx, const float *d_values,
+                           int strip_cols_opt, HostStrips &h)
+{
+    const int64_t M = p->M, N = p->N;
+    DevTmp tmp;
+    unsigned long long *nnz_d = nullptr;
+    int *bad = nullptr, *stats = nullptr;
+    int rc = tmp.get(&nnz_d, 1, true);
+    if (!rc) rc = tmp.get(&bad, 1, true);
+    if (!rc) rc = tmp.get(&stats, 2 * (size_t)std::max<int64_t>(M, 1), true);
+    if (rc) return rc;
+    const unsigned col_blocks = (unsigned)std::min<int64_t>(std::max<int64_t>((N + 7) / 8, 1), 148 * 16);
+    strips_check_kernel<<<col_blocks, 256>>>(d_col_ptr, d_row_idx, d_values, (int)M, (long long)N, nnz_d, bad);
+    SPMV_CUDA(cudaGetLastError());
+    unsigned long long nnz = 0;
+    int bad_h = 0;
+    SPMV_CUDA(cudaMemcpy(&nnz, nnz_d, sizeof nnz, cudaMemcpyDeviceToHost));
+    SPMV_CUDA(cudaMemcpy(&bad_h, bad, sizeof bad_h, cudaMemcpyDeviceToHost));
+    if (bad_h) return set_error(SPMV_ERR_ARG, "CSR(A^T) input: col_ptr must be monotone, the rows of a column in range and strictly ascending");
+    if (nnz >= (unsigned long long)UINT32_MAX) return set_error(SPMV_ERR_UNSUPPORTED, "strips: more than 2^32 entries");
+    const int sw = strip_cols_opt > 0 ? strip_cols_opt : choose_strip_cols(M, N, (int64_t)nnz);
+    if (sw < 32 || sw > kMaxStripCols || sw % 32) return set_error(SPMV_ERR_ARG, "strips: bad strip width %d", sw);
+    h.M = M; h.N = N; h.nnz = (int64_t)nnz; h.strip_cols = sw;
+    const int64_t band_cols = (int64_t)sw * kStripsPerBand;
+    h.bands = (int)std::max<int64_t>(1, (N + band_cols - 1) / band_cols);
+    const size_t segs = (size_t)h.bands * M * kStripsPerBand;
+    if (segs + 1 >= (size_t)UINT32_MAX * 8) return set_error(SPMV_ERR_UNSUPPORTED, "strips: too many row segments");
+
+    rc = plan_alloc(p, reinterpret_cast<void **>(&p->strips.soff), (segs + 1) * sizeof(uint32_t), true);
+    if (rc) return rc;
+    uint32_t *soff = p->strips.soff;
+    if (segs && nnz) {
+        strips_count_kernel<<<col_blocks, 256>>>(d_col_ptr, d_row_idx, d_values, (long long)M, (long long)N, sw, soff);
+        strips_pad_kernel<<<(unsigned)((segs + 255) / 256), 256>>>(soff, segs, (long long)M, stats, stats + M);
+        SPMV_CUDA(cudaGetLastError());
+    }
+    unsigned long long total = 0;
+    rc = exclusive_scan_u32(soff, soff, segs + 1, &total);
+    if (rc) return rc;
+    if (total >= (unsigned long long)UINT32_MAX) return set_error(SPMV_ERR_UNSUPPORTED, "strips: more than 2^32 stored entries");
+    // + 32 spare entries: an idle lane's (unread) source address stays legal (capi.cu: setup_strips)
+    rc = plan_alloc(p, reinterpret_cast<void **>(&p->strips.ent), ((size_t)total + 32) * sizeof(uint2), true);
+    if (rc) return rc;
+    if (total) {
+        uint32_t *cursor = nullptr;
+        rc = tmp.get(&cursor, segs, false);
+        if (rc) return rc;
+        SPMV_CUDA(cudaMemcpy(cursor, soff, segs * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+        strips_fill_kernel<<<(unsigned)(h.bands * kStripsPerBand), 256>>>(d_col_ptr, d_row_idx, d_values, (long long)M, (long long)N, sw,
+                                                                         cursor, p->strips.ent);
+        SPMV_CUDA(cudaGetLastError());
+    }
+    p->device_bytes += (int64_t)((segs + 1) * 4 + ((size_t)total + 32) * 8);
+    p->off_bytes = (int64_t)((segs + 1) * 4);
+    p->fmt_groups = (int64_t)total / kStripPad;
+    h.row_nnz.assign((size_t)M, 0); h.row_groups.assign((size_t)M, 0);
+    if (M > 0) {
+        SPMV_CUDA(cudaMemcpy(h.row_nnz.data(), stats, (size_t)M * 4, cudaMemcpyDeviceToHost));
+        SPMV_CUDA(cudaMemcpy(h.row_groups.data(), stats + M, (size_t)M * 4, cudaMemcpyDeviceToHost));
+    }
+    SPMV_CUDA(cudaDeviceSynchronize());
+    return SPMV_OK;
+}
+
+
 } // namespace spmv

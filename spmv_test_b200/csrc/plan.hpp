@@ -179,4 +179,7 @@ int plan_alloc(spmv_plan *p, void **slot, size_t bytes, bool zero);
 // the host packers; the Host* argument receives only what the geometry setup needs
 int pack_wsp_device(spmv_plan *p, const float *d_A, int64_t lda, int index_bits_opt, HostWsp &w);
 int pack_panel_device(spmv_plan *p, const float *d_A, int64_t lda, bool tiled, int slab_cols_opt, HostPanel &h);
+// row strips from CSR(A^T) in device memory (bit-identical to pack_strips_csc)
+int pack_strips_csc_device(spmv_plan *p, const int64_t *d_col_ptr, const int32_t *d_row_idx, const float *d_values,
+                           int strip_cols_opt, HostStrips &h);
 } // namespace spmv

@@ -88,6 +88,25 @@ class Plan:
                                          _opts(**opts), C.byref(h)))
         return cls(h.value)
 
+    @classmethod
+    def from_csc_device(cls, variant, M, N, col_ptr, row_idx, values, **opts):
+        """CSR(A^T) input as CUDA tensors (int64 col_ptr[N+1], int32 row_idx, float32 values) on the
+        current device: packed by kernels (row-strip form: variant "awsp", chunk_mode=4), bit-identical
+        to from_csc."""
+        import torch
+        if not (col_ptr.is_cuda and row_idx.is_cuda and values.is_cuda):
+            raise TypeError("col_ptr / row_idx / values must be CUDA tensors")
+        if col_ptr.dtype != torch.int64 or row_idx.dtype != torch.int32 or values.dtype != torch.float32:
+            raise TypeError("col_ptr int64, row_idx int32, values float32")
+        if col_ptr.numel() != N + 1:
+            raise ValueError("col_ptr needs N+1 entries")
+        col_ptr, row_idx, values = col_ptr.contiguous(), row_idx.contiguous(), values.contiguous()
+        h = C.c_void_p()
+        check(lib().spmv_plan_create_csc_device(VARIANTS[variant], M, N, C.c_void_p(col_ptr.data_ptr()),
+                                                C.c_void_p(row_idx.data_ptr() if row_idx.numel() else 0),
+                                                C.c_void_p(values.data_ptr() if values.numel() else 0), _opts(**opts), C.byref(h)))
+        return cls(h.value)
+
     def save(self, path):
         """Writes the packed format to `path` (no re-packing on load)."""
         check(lib().spmv_plan_save(self._h, str(path).encode()))

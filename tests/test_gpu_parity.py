@@ -648,3 +648,45 @@ def test_row_strips_row_ranges_and_zero_x(S):
     x1 = x0.copy(); x1[8999] = 2.0
     y = run_all(S, A, x1, variants=("awsp",), chunk_mode=4)["awsp"]
     assert np.array_equal(y, 2.0 * A[8999])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,density,sw", [(4096, 8192, 0.01, 0), (1000, 2048 + 96, 0.03, 64), (70000, 512, 0.01, 0),
+                                            (300, 40000, 0.01, 0), (33, 64, 0.5, 32), (5, 32, 0.0, 0)])
+def test_row_strips_device_packer_matches_host_packer(S, tmp_path, M, N, density, sw):
+    """spmv_plan_create_csc_device: CSR(A^T) arrays in device memory packed by kernels; the plan file is the
+    host packer's byte for byte, and bad input (unsorted / repeated / out-of-range rows) is rejected."""
+    import torch
+    from spmv_test_b200 import synth
+    if density > 0:
+        cp, ri, va = synth.bernoulli_csc(M, N, density, seed=77)
+    else:
+        cp, ri, va = np.zeros(N + 1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32)
+    if va.size > 10:
+        va[3] = 0.0                                        # an explicit zero is not stored
+        va[7] = -0.0
+    kw = {"slab_cols": sw} if sw else {}
+    x = ob.gen_vector(M, 0.5, 78)
+    with S.Plan.from_csc("awsp", M, N, cp, ri, va, chunk_mode=4, **kw) as ph, \
+            S.Plan.from_csc_device("awsp", M, N, torch.from_numpy(cp).cuda(), torch.from_numpy(ri).cuda(), torch.from_numpy(va).cuda(),
+                                   chunk_mode=4, **kw) as pd:
+        ph.save(tmp_path / "host.plan")
+        pd.save(tmp_path / "dev.plan")
+        assert (tmp_path / "host.plan").read_bytes() == (tmp_path / "dev.plan").read_bytes()
+        assert ph.run_host(x).tobytes() == pd.run_host(x).tobytes()
+        assert ph.traffic(x) == pd.traffic(x) and ph.info()["nnz"] == pd.info()["nnz"]
+    if ri.size > 4:
+        for bad in ("swap", "repeat", "range"):
+            r2 = ri.copy()
+            k = int(cp[np.argmax(np.diff(cp) >= 2)])       # first column with two entries
+            if bad == "swap":
+                r2[k], r2[k + 1] = r2[k + 1], r2[k]
+            elif bad == "repeat":
+                r2[k + 1] = r2[k]
+            else:
+                r2[k] = M
+            with pytest.raises(S.SpmvError):
+                S.Plan.from_csc_device("awsp", M, N, torch.from_numpy(cp).cuda(), torch.from_numpy(r2).cuda(),
+                                       torch.from_numpy(va).cuda(), chunk_mode=4, **kw)
+    with pytest.raises(S.SpmvError):                       # other forms are packed on the host
+        S.Plan.from_csc_device("awsp", M, N, torch.from_numpy(cp).cuda(), torch.from_numpy(ri).cuda(), torch.from_numpy(va).cuda())
