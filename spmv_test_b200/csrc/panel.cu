@@ -136,6 +136,9 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
 
     // ---- metadata of one 32-row block of a slab: lane = row ---------------------------------------
     struct Meta { float xv; uint32_t g0, g1; };
+    // (Round 2 A/B: visiting a slab's 32-row blocks with a stride coprime to the block count, so that a
+    // CTA's rows are spread over the whole slab, was SLOWER — config 2 awsp 21.3 vs 20.0 us, config 3
+    // 10.8 vs 9.9 — so the 1.5x spread between SMs is not an address effect; contiguous ranges stay.)
     auto load_meta = [&](int slab, int rb) {
         Meta m;
         const int row = rb * 32 + lane;
