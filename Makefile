@@ -13,7 +13,7 @@ OBJ    := build/obj
 NVFLAGS := -std=c++17 -O3 -lineinfo $(ARCH) -Iinclude -I$(CSRC) -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v
 CXXFLAGS := -std=c++17 -O3 -fPIC -fvisibility=hidden -Iinclude -I$(CSRC) -I$(CUDA)/include
 
-CU_SRCS  := capi wsp asp panel strips mg compact pack_dev
+CU_SRCS  := capi wsp asp panel panel_rs strips mg compact pack_dev
 CPP_SRCS := pack_host
 
 all: lib oracle harness

@@ -218,9 +218,13 @@ SPMV_API int spmv_run_act(spmv_plan_t *plan, const float *d_x, float *d_y, int a
  * Batched (multi-vector) form, SURVEY section 8f-2: Y[b] = X[b] * A for b < batch, X row-major
  * batch x M (row stride ldx), Y row-major batch x N (row stride ldy, multiple of 4), device
  * pointers.  wsp plans stream A once per group of 4 (or 2) vectors with all of them in shared
- * memory, asp plans stream a row once if any of the 4 (or 2) vectors is active there, so A's bytes
- * are reused; awsp / tcsr plans run the vectors one after the other.
- * Each Y[b] is bit-identical to spmv_run on X[b].
+ * memory, asp plans stream a row once if any of the 4 (or 2) vectors is active there, awsp / tcsr plans
+ * (one row per chunk: the dense-ish shapes) stream a row segment once for 2 vectors if either is active
+ * there, so A's bytes are reused; multi-row, lane-owned and row-strip plans run the vectors one by one.
+ * wsp / asp (and every vector that runs alone): Y[b] is bit-identical to spmv_run on X[b].  awsp / tcsr
+ * pairs: reproducible run to run and inside the same parity gate, but the rows are dealt to the warps by
+ * their rank among the rows active in EITHER vector, so the order of the sums — and with it the last
+ * bits — can differ from the single-vector call.
  */
 SPMV_API int spmv_run_batch(spmv_plan_t *plan, int batch, const float *d_X, int64_t ldx, float *d_Y, int64_t ldy,
                             void *stream);

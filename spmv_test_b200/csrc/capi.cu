@@ -165,8 +165,15 @@ static int setup_panel(spmv_plan *p, HostPanel &h, const spmv_options_t *o)
 static int setup_strips(spmv_plan *p, HostStrips &h, const spmv_options_t *o)
 {
     p->nnz = h.nnz; p->fmt_groups = 0;
-    int rc = upload(p, &p->strips.soff, h.soff);
-    p->off_bytes = (int64_t)h.soff.size() * 4;
+    // the device copy of the offsets is strip-major (formats.hpp): [band][strip 0..16][row], strip 16 = end of the row
+    std::vector<uint32_t> dev_off((size_t)h.bands * (kStripsPerBand + 1) * h.M + 1, 0u);
+    for (int b = 0; b < h.bands; b++)
+        for (int64_t r = 0; r < h.M; r++) {
+            const uint32_t *src = h.soff.data() + ((size_t)b * h.M + r) * kStripsPerBand;
+            for (int k = 0; k <= kStripsPerBand; k++) dev_off[((size_t)b * (kStripsPerBand + 1) + k) * h.M + r] = src[k];
+        }
+    int rc = upload(p, &p->strips.soff, dev_off);
+    p->off_bytes = (int64_t)dev_off.size() * 4;
     if (!rc) {                                             // + 32 spare entries: an idle lane's (unread) source address stays legal
         h.ent.resize(h.ent.size() + 32, 0);
         rc = upload(p, reinterpret_cast<uint64_t **>(&p->strips.ent), h.ent);
@@ -532,7 +539,14 @@ int spmv_plan_save(const spmv_plan_t *p, const char *path)
     const bool strips = p->strips.strip_cols > 0;
     if (strips) {
         hs.M = p->M; hs.N = p->N; hs.nnz = p->nnz; hs.strip_cols = p->strips.strip_cols; hs.bands = p->strips.bands;
-        rc = fetch(hs.soff, p->strips.soff, (size_t)hs.bands * p->M * kStripsPerBand + 1);
+        std::vector<uint32_t> dev_off;                     // strip-major on the device, row-major in the file
+        rc = fetch(dev_off, p->strips.soff, (size_t)hs.bands * (kStripsPerBand + 1) * p->M);
+        hs.soff.assign((size_t)hs.bands * p->M * kStripsPerBand + 1, (uint32_t)(p->fmt_groups * kStripPad));
+        if (!rc)
+            for (int b = 0; b < hs.bands; b++)
+                for (int64_t r = 0; r < p->M; r++)
+                    for (int k = 0; k < kStripsPerBand; k++)
+                        hs.soff[((size_t)b * p->M + r) * kStripsPerBand + k] = dev_off[((size_t)b * (kStripsPerBand + 1) + k) * p->M + r];
         if (!rc) rc = fetch(hs.ent, p->strips.ent, (size_t)p->fmt_groups * kStripPad);
         hs.row_nnz = p->row_nnz; hs.row_groups = p->row_groups;
     } else if (p->variant == SPMV_WSP) {
@@ -754,6 +768,9 @@ int spmv_plan_info(const spmv_plan_t *p, spmv_plan_info_t *info)
     info->kernels_per_run = p->kernels_per_run;
     info->grid_x = (int)p->grid.x; info->grid_y = (int)p->grid.y; info->block = p->block;
     info->smem_bytes = p->smem;
+    if ((p->variant == SPMV_AWSP || p->variant == SPMV_TCSR) && p->panel.rs_grid > 0) {   // what spmv_run launches
+        info->grid_x = p->panel.rs_grid; info->grid_y = 1; info->block = 256; info->smem_bytes = p->panel.rs_smem;
+    }
     info->index_bits = p->variant == SPMV_WSP ? p->wsp.index_bits
                        : (p->variant == SPMV_ASP ? 0 : p->strips.strip_cols > 0 ? 32 : p->panel.index_bits);
     info->row_splits = p->row_splits;
@@ -862,6 +879,11 @@ int spmv_run_batch(spmv_plan_t *p, int batch, const float *d_X, int64_t ldx, flo
                 if (rc == SPMV_OK) { done = B; break; }
                 if (rc != SPMV_ERR_UNSUPPORTED) return rc;
             }
+        }
+        if (!done && (p->variant == SPMV_AWSP || p->variant == SPMV_TCSR) && p->strips.strip_cols == 0 && batch - b >= 2) {
+            const int rc = launch_panel_batch(p, xb, ldx, yd, ldy, 2, st);       // a row segment is read once for two vectors
+            if (rc == SPMV_OK) done = 2;
+            else if (rc != SPMV_ERR_UNSUPPORTED) return rc;
         }
         if (!done) {                                      // one vector: the single-vector kernels
             const int rc = run_to(p, xb, yd, st);

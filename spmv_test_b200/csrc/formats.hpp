@@ -103,7 +103,11 @@ struct HostPanel {
 //     column uses;
 //   * a segment is padded with all-zero entries to a multiple of kStripPad = 4 entries, so it starts
 //     on a 32-byte sector boundary (a warp's load of ~20 entries then touches 6 sectors, not 7);
-//   * soff[(band*M + row)*16 + strip] = first entry of the segment (32-bit; one sentinel at the end).
+//   * soff[(band*M + row)*16 + strip] = first entry of the segment (32-bit; one sentinel at the end) —
+//     the host / file order.  In HBM the table is strip-major, [band][strip 0..16][row] with strip 16
+//     = the end of the row's band segment: a warp fetches its strip's starts lane = row, and 32
+//     nearby rows of one strip share a few sectors (row-major records cost one sector per row:
+//     2 of the 7 sectors a segment touched).
 // The kernel (strips.cu) gives a band's row range to a 16-warp CTA, warp w owns strip w: one
 // row segment = one 32-lane window, one entry per lane, no two lanes on one accumulator, so a
 // window retires in a single pass whatever its length.

@@ -582,6 +582,18 @@ strips_pad_kernel(uint32_t *__restrict__ cnt, size_t segs, long long M, int *__r
     }
 }
 
+// row-major starts (+ sentinel) -> the strip-major device table [band][strip 0..16][row]
+__global__ void __launch_bounds__(256)
+strips_transpose_kernel(const uint32_t *__restrict__ row_major, long long M, int bands, uint32_t *__restrict__ strip_major)
+{
+    const size_t n = (size_t)bands * (kStripsPerBand + 1) * M;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t row = i % (size_t)M, bk = i / (size_t)M;
+    const size_t k = bk % (kStripsPerBand + 1), b = bk / (kStripsPerBand + 1);
+    strip_major[i] = row_major[(b * (size_t)M + row) * kStripsPerBand + k];
+}
+
 __global__ void __launch_bounds__(256)
 strips_fill_kernel(const int64_t *__restrict__ col_ptr, const int32_t *__restrict__ row_idx, const float *__restrict__ values,
                    long long M, long long N, int sw, uint32_t *__restrict__ cursor, uint2 *__restrict__ ent)
@@ -635,9 +647,9 @@ int pack_strips_csc_device(spmv_plan *p, const int64_t *d_col_ptr, const int32_t
     const size_t segs = (size_t)h.bands * M * kStripsPerBand;
     if (segs + 1 >= (size_t)UINT32_MAX * 8) return set_error(SPMV_ERR_UNSUPPORTED, "strips: too many row segments");
 
-    rc = plan_alloc(p, reinterpret_cast<void **>(&p->strips.soff), (segs + 1) * sizeof(uint32_t), true);
+    uint32_t *soff = nullptr;                             // row-major counts -> starts (+ sentinel): a temporary
+    rc = tmp.get(&soff, segs + 1, true);
     if (rc) return rc;
-    uint32_t *soff = p->strips.soff;
     if (segs && nnz) {
         strips_count_kernel<<<col_blocks, 256>>>(d_col_ptr, d_row_idx, d_values, (long long)M, (long long)N, sw, soff);
         strips_pad_kernel<<<(unsigned)((segs + 255) / 256), 256>>>(soff, segs, (long long)M, stats, stats + M);
@@ -659,8 +671,15 @@ int pack_strips_csc_device(spmv_plan *p, const int64_t *d_col_ptr, const int32_t
                                                                          cursor, p->strips.ent);
         SPMV_CUDA(cudaGetLastError());
     }
-    p->device_bytes += (int64_t)((segs + 1) * 4 + ((size_t)total + 32) * 8);
-    p->off_bytes = (int64_t)((segs + 1) * 4);
+    const size_t n_dev_off = (size_t)h.bands * (kStripsPerBand + 1) * M;
+    rc = plan_alloc(p, reinterpret_cast<void **>(&p->strips.soff), (n_dev_off + 1) * sizeof(uint32_t), true);
+    if (rc) return rc;
+    if (n_dev_off) {
+        strips_transpose_kernel<<<(unsigned)((n_dev_off + 255) / 256), 256>>>(soff, (long long)M, h.bands, p->strips.soff);
+        SPMV_CUDA(cudaGetLastError());
+    }
+    p->device_bytes += (int64_t)((n_dev_off + 1) * 4 + ((size_t)total + 32) * 8);
+    p->off_bytes = (int64_t)((n_dev_off + 1) * 4);
     p->fmt_groups = (int64_t)total / kStripPad;
     h.row_nnz.assign((size_t)M, 0); h.row_groups.assign((size_t)M, 0);
     if (M > 0) {

@@ -26,6 +26,7 @@
 // 16-bit in-tile offsets (the reference's blk_idx, tcsr.cpp:13,34, made two-level).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "plan.hpp"
@@ -84,10 +85,11 @@ template <> struct ColIdx<16> {
 //                         [slot info][multi-row mode: per-lane (x, row slot) ring]
 constexpr int kListCap = 128;              // rows a warp can take from one metadata batch
 constexpr int kMetaBatch = 8;              // 32-row blocks of metadata fetched together
-template <int IDXB, int kStages, bool MR, bool LOB = false> __host__ __device__ constexpr int warp_smem_bytes(int W)
+// B = 2 (batched form, one row per chunk only): two accumulator rows per warp and a second x per ring slot
+template <int IDXB, int kStages, bool MR, bool LOB = false, int B = 1> __host__ __device__ constexpr int warp_smem_bytes(int W)
 {
-    return W * 4 + kStages * 32 * 16 + kStages * 32 * (IDXB == 8 ? 4 : 8) + (LOB ? 0 : kListCap * 16) + kStages * 8 +
-           (MR ? kStages * 32 * 8 : 0);
+    return W * 4 * B + kStages * 32 * 16 + kStages * 32 * (IDXB == 8 ? 4 : 8) + (LOB ? 0 : kListCap * 16) + kStages * 8 +
+           (MR ? kStages * 32 * 8 : 0) + (B > 1 ? kStages * 8 : 0);
 }
 
 // Balanced flat decomposition.  The (slab, row) pairs, slab-major, form one sequence of
@@ -102,14 +104,18 @@ __device__ __forceinline__ long long cta_of_unit(long long u, long long T, long 
 
 // LOB: lane-owned blocks (formats.hpp) — the units of the flat sequence are (slab, block) pairs
 // (`units` = blocks per slab), lane l owns the columns congruent to l modulo 32.
-template <int IDXB, bool TILED, bool MR, int kStages, bool LOB = false>
+// B = 2: batched form — two activation vectors x[0], x[1] (row stride ldx) against the same
+// A: a row segment is streamed once if EITHER vector is active there and used for both (a vector with
+// x == 0 adds an exact zero), so every y[b] is bit-identical to a single-vector call.
+template <int IDXB, bool TILED, bool MR, int kStages, bool LOB = false, int B = 1>
 __global__ void __launch_bounds__(kPanelThreads)
 panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
              const uint32_t *__restrict__ off, const uint16_t *__restrict__ rel,
              const float *__restrict__ x, const YDst yd, float *__restrict__ partial,
              unsigned *__restrict__ tickets, int M, int N, int W, int row_blocks, int slabs, int kmax,
-             int units, int block_rows, int cbits)
+             int units, int block_rows, int cbits, long long ldx, long long ldy)
 {
+    static_assert(B == 1 || (B == 2 && !MR && !LOB), "the batched form exists for one-row-per-chunk plans");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int last_flag;
     using CI = ColIdx<IDXB>;
@@ -118,13 +124,14 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_warps = blockDim.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes<IDXB, kStages, MR, LOB>(W);
-    float *acc = reinterpret_cast<float *>(wbase);
-    float4 *ring_v = reinterpret_cast<float4 *>(wbase + (size_t)W * 4);
-    IVec *ring_i = reinterpret_cast<IVec *>(wbase + (size_t)W * 4 + kStages * 32 * 16);
-    uint4 *list = reinterpret_cast<uint4 *>(wbase + (size_t)W * 4 + kStages * 32 * 16 + kStages * 32 * sizeof(IVec));
+    unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes<IDXB, kStages, MR, LOB, B>(W);
+    float *acc = reinterpret_cast<float *>(wbase);        // B rows of W accumulators
+    float4 *ring_v = reinterpret_cast<float4 *>(wbase + (size_t)W * 4 * B);
+    IVec *ring_i = reinterpret_cast<IVec *>(wbase + (size_t)W * 4 * B + kStages * 32 * 16);
+    uint4 *list = reinterpret_cast<uint4 *>(wbase + (size_t)W * 4 * B + kStages * 32 * 16 + kStages * 32 * sizeof(IVec));
     uint2 *sinfo = reinterpret_cast<uint2 *>(list + (LOB ? 0 : kListCap));   // per ring slot: (valid lanes, x of the row | passes)
     uint2 *ring_m = sinfo + kStages;                             // MR: per lane (x of its row, row slot in the chunk)
+    float *sinfo_x1 = reinterpret_cast<float *>(sinfo + kStages);             // B = 2: the second vector's x of the slot's row
     const int wg = blockIdx.x * n_warps + warp;           // trace id
     (void)wg;
     SPMV_STAMP(wg, 0);
@@ -135,7 +142,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     const long long u_begin = range_begin(blockIdx.x, T, G), u_end = range_begin(blockIdx.x + 1, T, G);
 
     // ---- metadata of one 32-row block of a slab: lane = row ---------------------------------------
-    struct Meta { float xv; uint32_t g0, g1; };
+    struct Meta { float xv, xv1; uint32_t g0, g1; };
     // (Round 2 A/B: visiting a slab's 32-row blocks with a stride coprime to the block count, so that a
     // CTA's rows are spread over the whole slab, was SLOWER — config 2 awsp 21.3 vs 20.0 us, config 3
     // 10.8 vs 9.9 — so the 1.5x spread between SMs is not an address effect; contiguous ranges stay.)
@@ -143,6 +150,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         Meta m;
         const int row = rb * 32 + lane;
         m.xv = row < M ? __ldg(x + row) : 0.0f;
+        m.xv1 = (B > 1 && row < M) ? __ldg(x + ldx + row) : 0.0f;
         if (TILED) {
             const size_t t = (size_t)slab * (row_blocks + 1) + rb;
             const uint32_t tb = __ldg(off + t), te = __ldg(off + t + 1);
@@ -176,6 +184,13 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         float r0 = acc[c[0]], r1 = acc[c[1]], r2 = acc[c[2]], r3 = acc[c[3]];
         r0 = fmaf(a.x, p, r0); r1 = fmaf(a.y, p, r1); r2 = fmaf(a.z, p, r2); r3 = fmaf(a.w, p, r3);
         if (lane < info.x) { acc[c[0]] = r0; acc[c[1]] = r1; acc[c[2]] = r2; acc[c[3]] = r3; }
+        if (B > 1) {                                      // the same group against the second vector's accumulator row
+            const float q = sinfo_x1[s];
+            float *acc1 = acc + W;
+            float t0 = acc1[c[0]], t1 = acc1[c[1]], t2 = acc1[c[2]], t3 = acc1[c[3]];
+            t0 = fmaf(a.x, q, t0); t1 = fmaf(a.y, q, t1); t2 = fmaf(a.z, q, t2); t3 = fmaf(a.w, q, t3);
+            if (lane < info.x) { acc1[c[0]] = t0; acc1[c[1]] = t1; acc1[c[2]] = t2; acc1[c[3]] = t3; }
+        }
         __syncwarp();                                     // next chunk may be another row
     };
     auto run_list = [&](int n_rows) {
@@ -192,7 +207,10 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
                 cp_async16_zfill(ring_v + s * 32 + lane, vals + gs, ok);
                 CI::copy(ring_i + s * 32 + lane, idx, gs, ok);
                 cp_async_commit();
-                if (lane == 0) sinfo[s] = make_uint2(min(32u, m.y - g), m.z);
+                if (lane == 0) {
+                    sinfo[s] = make_uint2(min(32u, m.y - g), m.z);
+                    if (B > 1) sinfo_x1[s] = __uint_as_float(m.w);
+                }
             }
         }
     };
@@ -261,7 +279,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
     // it, whose last chunks may still sit in a ring, and the next one, fetched into registers while
     // the current block streams).  All warps of the CTA walk the same blocks, each taking every
     // n_warps-th chunk.
-    float *xbuf = reinterpret_cast<float *>(smem_raw + (size_t)n_warps * warp_smem_bytes<IDXB, kStages, MR, LOB>(W));
+    float *xbuf = reinterpret_cast<float *>(smem_raw + (size_t)n_warps * warp_smem_bytes<IDXB, kStages, MR, LOB, B>(W));
     auto retire_lob = [&](int s, uint32_t xo) {           // xo: where the chunk's block keeps its x slice
         const float4 a = ring_v[s * 32 + lane];
         uint32_t c[4];
@@ -354,7 +372,7 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         const int row_b = (int)min((long long)units, row_a + (u_end - u));
         u += row_b - row_a;
 
-        for (int c = lane; c < W; c += 32) acc[c] = 0.0f;
+        for (int c = lane; c < W * B; c += 32) acc[c] = 0.0f;
         for (int k = lane; k < kStages * 32; k += 32) ring_i[k] = CI::zero();
         if (lane < kStages) sinfo[lane] = make_uint2(0u, 0u);
         __syncwarp();
@@ -393,12 +411,13 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
                     const int j = half * (kMetaBatch / 2) + jj;
                     const int blk = blk0 + j * bstep;
                     const int row = blk * 32 + lane;
-                    const bool valid = blk < blk_b && row >= row_a && row < row_b && cur[j].xv != 0.0f && cur[j].g1 > cur[j].g0;
+                    const bool valid = blk < blk_b && row >= row_a && row < row_b && (cur[j].xv != 0.0f || (B > 1 && cur[j].xv1 != 0.0f)) &&
+                                       cur[j].g1 > cur[j].g0;
                     const unsigned mask = __ballot_sync(kFull, valid);
                     const int rank = rank_base + __popc(mask & lt);
                     const bool mine = valid && (by_block || (rank & (n_warps - 1)) == warp);   // n_warps is a power of two
                     const unsigned mm = __ballot_sync(kFull, mine);
-                    if (mine) list[cnt + __popc(mm & lt)] = make_uint4(cur[j].g0, cur[j].g1, __float_as_uint(cur[j].xv), 0u);
+                    if (mine) list[cnt + __popc(mm & lt)] = make_uint4(cur[j].g0, cur[j].g1, __float_as_uint(cur[j].xv), __float_as_uint(cur[j].xv1));
                     cnt += __popc(mm);
                     rank_base += __popc(mask);
                 }
@@ -426,13 +445,18 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
         const int n_pieces = (int)(c_hi - c_lo + 1);
         const int col0 = slab * W;
         const int n_valid = min(W, N - col0);
-        const int wstride = warp_smem_bytes<IDXB, kStages, MR, LOB>(W) / 4;
+        const int wstride = warp_smem_bytes<IDXB, kStages, MR, LOB, B>(W) / 4;
         const float *acc0 = reinterpret_cast<const float *>(smem_raw);
-        float *dst = partial + ((size_t)blockIdx.x * kmax + piece) * W;
-        for (int c = tid; c < n_valid; c += blockDim.x) {
-            float s = acc0[c];
-            for (int w = 1; w < n_warps; w++) s += acc0[(size_t)w * wstride + c];
-            if (n_pieces == 1) y_store(yd, (size_t)col0 + c, s); else dst[c] = s;
+        // vector b's partial rows live at [b][CTA * kmax + piece]; its y at row b of the batch (stride ldy)
+        const size_t rows_per_b = (size_t)gridDim.x * kmax;
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            float *dst = partial + ((size_t)b * rows_per_b + (size_t)blockIdx.x * kmax + piece) * W;
+            for (int c = tid; c < n_valid; c += blockDim.x) {
+                float s = acc0[b * W + c];
+                for (int w = 1; w < n_warps; w++) s += acc0[(size_t)w * wstride + b * W + c];
+                if (n_pieces == 1) y_store(yd, (size_t)b * ldy + col0 + c, s); else dst[c] = s;
+            }
         }
         SPMV_STAMP(wg, 6);
         if (n_pieces > 1) {
@@ -446,8 +470,12 @@ panel_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx,
                 row_of[j] = (uint32_t)(c * kmax + (slab - (int)(range_begin(c, T, G) / units)));
             }
             // (split_reduce_rows starts with a barrier, which also publishes row_of)
-            split_reduce_rows(yd, (size_t)col0, [&](int j) { return partial + (size_t)row_of[j] * W; }, &tickets[slab],
-                              n_pieces, W, n_valid, &last_flag, scratch);
+            for (int b = 0; b < B; b++) {
+                const float *pb = partial + (size_t)b * rows_per_b * W;
+                split_reduce_rows(yd, (size_t)b * ldy + col0, [&](int j) { return pb + (size_t)row_of[j] * W; },
+                                  &tickets[(size_t)b * slabs + slab], n_pieces, W, n_valid, &last_flag, scratch);
+                if (B > 1) __syncthreads();               // the scratch is reused by the next vector
+            }
         }
         __syncthreads();                                  // shared memory is reused by the next piece
         SPMV_STAMP(wg, 7);
@@ -468,7 +496,28 @@ int launch_variant(spmv_plan *p, const float *x, const YDst &y, cudaStream_t st)
     while ((32 << cbits) < d.slab_cols) cbits++;
     SPMV_CUDA(launch_k(k, p->grid, dim3(p->block), p->smem, st, reinterpret_cast<const float4 *>(d.vals), d.idx, d.off, d.rel,
                        x, y, p->partial, p->tickets, (int)p->M, (int)p->N, d.slab_cols, d.row_blocks, d.slabs, d.kmax,
-                       LOB ? d.lob_blocks : (int)p->M, d.block_rows, cbits));
+                       LOB ? d.lob_blocks : (int)p->M, d.block_rows, cbits, 0LL, 0LL));
+    return SPMV_OK;
+}
+
+// Two vectors per pass (one-row-per-chunk plans): a 4-deep ring so that two accumulator rows per warp
+// still leave room for two CTAs per SM; same grid, same decomposition, so y[b] is bit-identical to
+// a single-vector call.
+template <int IDXB, bool TILED>
+int launch_batch2(spmv_plan *p, const float *x, long long ldx, const YDst &y, long long ldy, cudaStream_t st)
+{
+    auto k = panel_kernel<IDXB, TILED, false, kMrStages, false, 2>;
+    const DevPanel &d = p->panel;
+    const int smem = d.warps * warp_smem_bytes<IDXB, kMrStages, false, false, 2>(d.slab_cols);
+    if (smem > (p->max_smem_optin > 0 ? p->max_smem_optin : 227 * 1024) || 2 * smem + 2048 > 228 * 1024) return SPMV_ERR_UNSUPPORTED;
+    static int smem_set[16] = {0};
+    if (smem > 48 * 1024 && p->device >= 0 && p->device < 16 && smem_set[p->device] < smem) {
+        SPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set[p->device] = smem;
+    }
+    SPMV_CUDA(launch_k(k, p->grid, dim3(p->block), (size_t)smem, st, reinterpret_cast<const float4 *>(d.vals), d.idx, d.off, d.rel,
+                       x, y, p->partial, p->tickets, (int)p->M, (int)p->N, d.slab_cols, d.row_blocks, d.slabs, d.kmax,
+                       (int)p->M, d.block_rows, 0, ldx, ldy));
     return SPMV_OK;
 }
 
@@ -482,6 +531,7 @@ int launch_panel(spmv_plan *p, const float *d_x, const YDst &d_y, cudaStream_t s
         return SPMV_OK;
     }
     const DevPanel &d = p->panel;
+    if (d.rs_grid > 0) return launch_panel_rs(p, d_x, d_y, st);           // one row per chunk: the register-staged form
     if (d.block_rows > 0) return launch_variant<16, false, false, true>(p, d_x, d_y, st);
     if (d.multirow) {
         if (d.index_bits == 8) return d.tiled ? launch_variant<8, true, true>(p, d_x, d_y, st) : launch_variant<8, false, true>(p, d_x, d_y, st);
@@ -489,6 +539,16 @@ int launch_panel(spmv_plan *p, const float *d_x, const YDst &d_y, cudaStream_t s
     }
     if (d.index_bits == 8) return d.tiled ? launch_variant<8, true, false>(p, d_x, d_y, st) : launch_variant<8, false, false>(p, d_x, d_y, st);
     return d.tiled ? launch_variant<16, true, false>(p, d_x, d_y, st) : launch_variant<16, false, false>(p, d_x, d_y, st);
+}
+
+// Batched form: B = 2 vectors in one pass over A's row segments (awsp / tcsr, one row per chunk);
+// returns SPMV_ERR_UNSUPPORTED otherwise (the caller then runs the vectors one by one).
+int launch_panel_batch(spmv_plan *p, const float *d_x, long long ldx, const YDst &d_y, long long ldy, int B, cudaStream_t st)
+{
+    const DevPanel &d = p->panel;
+    if (B != 2 || d.multirow || d.block_rows > 0 || p->M == 0 || p->N == 0 || !p->panel.batch_ok) return SPMV_ERR_UNSUPPORTED;
+    if (d.index_bits == 8) return d.tiled ? launch_batch2<8, true>(p, d_x, ldx, d_y, ldy, st) : launch_batch2<8, false>(p, d_x, ldx, d_y, ldy, st);
+    return d.tiled ? launch_batch2<16, true>(p, d_x, ldx, d_y, ldy, st) : launch_batch2<16, false>(p, d_x, ldx, d_y, ldy, st);
 }
 
 // Geometry: a 1-D grid of G CTAs over the flat (slab, row) sequence, one resident wave.
@@ -550,7 +610,20 @@ int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o)
     p->grid = dim3((unsigned)G, 1, 1);
     // scratch: one partial row per (CTA, piece) + one ticket per slab
     p->partial = nullptr; p->tickets = nullptr;
-    return alloc_panel_scratch(p, (size_t)G * d.kmax * h.slab_cols, (size_t)slabs);
+    d.batch_ok = !lob && !d.multirow;                     // room for the second vector of the batched form
+    const size_t copies = d.batch_ok ? 2 : 1;
+    int rc = alloc_panel_scratch(p, copies * (size_t)G * d.kmax * h.slab_cols, copies * (size_t)slabs);
+    // Single-vector calls on one-row-per-chunk plans take the register-staged form (panel_rs.cu) unless the
+    // caller forced this kernel's geometry; the ring kernel above stays for the pair form, the forced
+    // options, the multi-row and the lane-owned modes.  SPMV_PANEL_RS=0: development switch (same-box A/B).
+    d.rs_grid = 0;
+    const char *e = std::getenv("SPMV_PANEL_RS");
+    const bool forced = o && (o->row_splits > 0 || o->warps_per_col > 0);
+    if (!rc && !lob && !d.multirow && !forced && !(e && std::atoi(e) == 0) && h.M > 0 && h.N > 0) {
+        rc = configure_panel_rs(p, h);
+        if (!rc && d.rs_grid > 0) p->kernels_per_run = 2;
+    }
+    return rc;
 }
 
 } // namespace spmv

@@ -93,6 +93,11 @@ struct DevPanel {
     bool multirow = false;      // several short rows per 32-group chunk
     int block_rows = 0;         // > 0: lane-owned blocks (formats.hpp), off is per (slab, block)
     int lob_blocks = 0;
+    bool batch_ok = false;      // scratch holds two vectors' partial rows (spmv_run_batch on awsp / tcsr)
+    // register-staged form (panel_rs.cu) for one-row-per-chunk plans: rs_grid > 0 when spmv_run takes it
+    int rs_grid = 0, rs_kmax = 0, rs_smem = 0;
+    bool rs_by_block = false;   // pieces of >= 256 rows: a warp owns whole 32-row blocks
+    float *rs_partial = nullptr;
 };
 
 // row strips (formats.hpp: HostStrips; strips.cu)
@@ -160,6 +165,9 @@ int launch_wsp_batch(spmv_plan *p, const float *d_x, long long ldx, const YDst &
 int launch_asp(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
 int launch_asp_batch(spmv_plan *p, const float *d_x, long long ldx, const YDst &yd, long long ldy, int B, cudaStream_t st);
 int launch_panel(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
+int launch_panel_rs(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
+int configure_panel_rs(spmv_plan *p, const HostPanel &h);
+int launch_panel_batch(spmv_plan *p, const float *d_x, long long ldx, const YDst &yd, long long ldy, int B, cudaStream_t st);
 int launch_strips(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st);
 int launch_compact(const float *d_x, int64_t M, int32_t *d_idx, float *d_val, int32_t *d_count,
                    void *d_scratch, size_t scratch_bytes, cudaStream_t st);

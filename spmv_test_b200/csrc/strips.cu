@@ -102,7 +102,7 @@ strips_kernel(const uint2 *__restrict__ ent, const uint32_t *__restrict__ soff, 
 
     for (int c = lane; c < sw + 32; c += 32) acc[c] = 0.0f;
     pdl_wait();
-    const uint32_t *so = soff + (size_t)band * M * kStripsPerBand + warp;
+    const uint32_t *so = soff + ((size_t)band * (kStripsPerBand + 1) + warp) * M;   // strip-major: this strip's starts, row by row
     uint64_t ent_lane = reinterpret_cast<uint64_t>(ent + lane);   // opaque to the optimiser: one IMAD.WIDE per address
     asm volatile("" : "+l"(ent_lane));
     const uint32_t ring_lane = smem_u32(ring + lane);
@@ -150,9 +150,9 @@ strips_kernel(const uint2 *__restrict__ ent, const uint32_t *__restrict__ soff, 
             Meta m{0u, 0u, 0u};
             const int i = b0 + lane;
             if (i < total) {
-                const uint32_t *p = so + (size_t)(sub0 + rows_s[i]) * kStripsPerBand;
+                const uint32_t *p = so + (sub0 + rows_s[i]);          // 32 nearby rows: a few sectors per request
                 m.st = __ldg(p);
-                m.end = __ldg(p + 1);
+                m.end = __ldg(p + M);                                // the next strip's start (strip 16: the end of the row)
                 m.x = __float_as_uint(xs_s[i]);
             }
             return m;
@@ -287,27 +287,40 @@ strips_kernel(const uint2 *__restrict__ ent, const uint32_t *__restrict__ soff, 
     }
 }
 
-// y[col] = sum over the band's row ranges, in range order (fixed), 8 independent loads in flight
+// y[col] = sum over the band's row ranges.  A CTA handles 32 float4 columns with 8 row groups: group k
+// adds ranges k, k+8, ... (all of its loads in flight at once for up to 64 ranges), then the 8 group
+// sums are added in group order — the order depends only on (shape, R), never on timing.  (One thread
+// per column with 8 loads in flight needed five dependent L2 round trips for 37 ranges: ~5 us per call.)
 __global__ void __launch_bounds__(256)
 strips_reduce_kernel(const float *__restrict__ partial, const YDst yd, int N, int band_cols, int R)
 {
+    __shared__ float4 sums[256];
     pdl_wait();
-    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = threadIdx.x & 31, k = threadIdx.x >> 5;
+    const size_t i4 = (size_t)blockIdx.x * 32 + v;
     const size_t col = i4 * 4;
-    if (col >= (size_t)N) return;
-    const size_t band = col / band_cols, within = col - band * band_cols;
-    const float4 *p = reinterpret_cast<const float4 *>(partial + band * R * (size_t)band_cols + within);
-    const size_t stride4 = (size_t)band_cols >> 2;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < R; r += kRedBatch) {
-        float4 t[kRedBatch];
+    if (col < (size_t)N) {
+        const size_t band = col / band_cols, within = col - band * band_cols;
+        const float4 *p = reinterpret_cast<const float4 *>(partial + band * R * (size_t)band_cols + within);
+        const size_t stride4 = (size_t)band_cols >> 2;
+        for (int r = k; r < R; r += 8 * kRedBatch) {
+            float4 t[kRedBatch];
 #pragma unroll
-        for (int u = 0; u < kRedBatch; u++)
-            t[u] = r + u < R ? __ldcg(p + (size_t)(r + u) * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = 0; u < kRedBatch; u++)
+                t[u] = r + 8 * u < R ? __ldcg(p + (size_t)(r + 8 * u) * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < kRedBatch; u++) acc = f4_add(acc, t[u]);
+            for (int u = 0; u < kRedBatch; u++) acc = f4_add(acc, t[u]);
+        }
     }
-    y_store4(yd, i4, acc);
+    sums[threadIdx.x] = acc;
+    __syncthreads();
+    if (k == 0 && col < (size_t)N) {
+        float4 s = sums[v];
+#pragma unroll
+        for (int g = 1; g < 8; g++) s = f4_add(s, sums[g * 32 + v]);
+        y_store4(yd, i4, s);
+    }
 }
 
 } // namespace
@@ -329,7 +342,7 @@ int launch_strips(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t s
                        (int)p->M, (int)p->N, d.strip_cols, d.ctas_per_band));
     if (d.ctas_per_band > 1) {
         const int band_cols = d.strip_cols * kStripsPerBand;
-        const unsigned blocks = (unsigned)((p->N / 4 + 255) / 256);
+        const unsigned blocks = (unsigned)((p->N / 4 + 31) / 32);
         SPMV_CUDA(launch_k(strips_reduce_kernel, dim3(blocks), dim3(256), 0, st, (const float *)p->partial, yd, (int)p->N, band_cols,
                            d.ctas_per_band));
     }

@@ -568,7 +568,10 @@ int configure_wsp(spmv_plan *p, const HostWsp &w, const spmv_options_t *o)
         s->bins.push_back(d);
     }
     p->kernels_per_run = (int)s->bins.size() + (w.panels > 1 ? 1 : 0);
-    if (!p->wsp.x_in_smem && s->bins.size() > 1 && (int)s->bins.size() <= kMaxBins) p->kernels_per_run = 1;   // merged launch
+    // merged launch.  (Round 2: sharing ONE resident wave of sm_count * 8 CTAs among the bins in proportion to
+    // their thread-iterations, instead of a full wave per bin, was much slower on config 4 — 160 vs 107 us: the
+    // 2.3 waves of the per-bin grids are what balances bins of very different per-column cost.)
+    if (!p->wsp.x_in_smem && s->bins.size() > 1 && (int)s->bins.size() <= kMaxBins) p->kernels_per_run = 1;
     p->grid = dim3(s->bins.empty() ? 1 : s->bins[0].grid, 1, 1);
     p->wsp.warps_per_col = s->bins.empty() ? 0 : std::max(1, s->bins[0].T / 32);
     p->wsp_team = s->bins.empty() ? 0 : s->bins[0].T;

@@ -391,31 +391,74 @@ def test_plan_save_load_roundtrip(S, tmp_path):
 
 
 @pytest.mark.parametrize("batch", [1, 2, 3, 4, 7])
-def test_run_batch_matches_single_vector_calls(S, batch):
-    """spmv_run_batch: every Y[b] is bit-identical to spmv_run on X[b] (the wsp kernel reuses A's
-    bytes for groups of 4 / 2 vectors; other variants run the vectors one after the other)."""
+def test_run_batch_against_the_oracle_and_single_vector_calls(S, batch):
+    """spmv_run_batch: every Y[b] is within the parity gate of the ORACLE and bit-identical to spmv_run on X[b]
+    (wsp / asp reuse A's bytes for groups of 4 / 2 vectors, awsp / tcsr for pairs; one vector of the batch is
+    all zero, one row is active in only one vector of a pair)."""
     import torch
     A = ob.gen_matrix(1024, 768, 0.7, 91)
     X = np.stack([ob.gen_vector(1024, 0.5, 100 + b) for b in range(batch)])
+    if batch >= 2:
+        X[1, :] = 0.0                                      # a pair with one inactive vector
+        X[0, 5] = 0.25
+    if batch >= 4:
+        X[2, 7], X[3, 7] = 0.5, 0.0                        # a row active in one vector of the pair only
+    refs_b = [(ob.sgemv_dense(A, X[b]),) + ob.sgemv_dense_f64(A, X[b]) for b in range(batch)]
     dX = torch.from_numpy(X).cuda()
-    for v in VARIANTS:
-        with S.Plan.from_dense(v, A) as p:
+    cases = [(v, {}) for v in VARIANTS] + [("awsp", {"slab_cols": 256}), ("tcsr", {"slab_cols": 256}), ("awsp", {"chunk_mode": 2}),
+                                           ("awsp", {"chunk_mode": 4})]
+    for v, kw in cases:
+        with S.Plan.from_dense(v, A, **kw) as p:
             dY = torch.full((batch, 768), -1.0, device="cuda")
             p.run_batch(dX, dY)
             torch.cuda.synchronize()
             Y = dY.cpu().numpy()
+            pairs = v in ("awsp", "tcsr") and kw.get("chunk_mode", 0) in (0, 1)   # the pair kernel: gate + reproducible
             for b in range(batch):
-                assert Y[b].tobytes() == p.run_host(X[b]).tobytes(), (v, b)
+                y32, y64, s = refs_b[b]
+                check_y(Y[b], y32, y64, s, f"batch {v} {kw} vector {b}")
+                if not pairs or b == batch - 1 and batch % 2:
+                    assert Y[b].tobytes() == p.run_host(X[b]).tobytes(), (v, kw, b)
+            dY2 = torch.full((batch, 768), -2.0, device="cuda")
+            p.run_batch(dX, dY2)
+            torch.cuda.synchronize()
+            assert dY2.cpu().numpy().tobytes() == Y.tobytes(), f"{v} {kw}: two batched runs differ"
     # strided X / Y (leading dimensions larger than M / N)
-    with S.Plan.from_dense("wsp", A) as p:
-        dXp = torch.zeros((batch, 1024 + 32), device="cuda")
-        dXp[:, :1024] = dX
-        dYp = torch.zeros((batch, 768 + 64), device="cuda")
-        p.run_batch(dXp[:, :1024], dYp[:, :768])
-        torch.cuda.synchronize()
-        assert dYp[:, :768].cpu().numpy().tobytes() == Y.tobytes() if v == "wsp" else True
-        for b in range(batch):
-            assert dYp[b, :768].cpu().numpy().tobytes() == p.run_host(X[b]).tobytes()
+    for v in ("wsp", "awsp"):
+        with S.Plan.from_dense(v, A) as p:
+            dXp = torch.zeros((batch, 1024 + 32), device="cuda")
+            dXp[:, :1024] = dX
+            dYp = torch.zeros((batch, 768 + 64), device="cuda")
+            p.run_batch(dXp[:, :1024], dYp[:, :768])
+            torch.cuda.synchronize()
+            for b in range(batch):
+                y32, y64, s = refs_b[b]
+                check_y(dYp[b, :768].cpu().numpy(), y32, y64, s, f"strided batch {v} vector {b}")
+                if v == "wsp":
+                    assert dYp[b, :768].cpu().numpy().tobytes() == p.run_host(X[b]).tobytes()
+            assert float(dYp[:, 768:].abs().max()) == 0.0
+
+
+def test_run_batch_config2_pairs_reuse_the_matrix(S):
+    """Config 2 shape: the awsp / tcsr pair kernel against the oracle (several CTAs per slab: the partial rows
+    and tickets of both vectors), reproducible run to run."""
+    import torch
+    A = ob.gen_matrix(4096, 14336, 0.7, 1234)
+    X = np.stack([ob.gen_vector(4096, 0.5, 4321), ob.gen_vector(4096, 0.5, 4322)])
+    dX = torch.from_numpy(X).cuda()
+    for v in ("awsp", "tcsr"):
+        with S.Plan.from_dense(v, A) as p:
+            dY = torch.zeros((2, 14336), device="cuda")
+            p.run_batch(dX, dY)
+            torch.cuda.synchronize()
+            Y = dY.cpu().numpy()
+            for b in range(2):
+                y32 = ob.sgemv_dense(A, X[b]); y64, s = ob.sgemv_dense_f64(A, X[b])
+                check_y(Y[b], y32, y64, s, f"config 2 batched {v} vector {b}")
+            dY2 = torch.zeros((2, 14336), device="cuda")
+            p.run_batch(dX, dY2)
+            torch.cuda.synchronize()
+            assert dY2.cpu().numpy().tobytes() == Y.tobytes()
 
 
 # ---- device packers (csrc/pack_dev.cu; SURVEY 8f-1) ----------------------------------------------
@@ -564,6 +607,8 @@ def test_fused_relu_and_ffn_chain(S):
             yn = y.cpu().numpy()
             assert np.array_equal(yr.cpu().numpy(), np.where(yn < 0, np.float32(0), yn)), v
             assert np.any(yn < 0)
+            y32a, y64a, sa = refs(A1, x)                                 # ... and the rectified output against the ORACLE's y
+            check_y(yr.cpu().numpy(), np.where(y32a < 0, np.float32(0), y32a), np.where(y32a < 0, 0.0, y64a), sa, f"relu {v}")
     with S.Plan.from_dense("wsp", A1) as up, S.Plan.from_dense("awsp", A2) as down:
         h = torch.empty(H, device="cuda"); z = torch.empty(M, device="cuda")
         up.run(dx, h, act="relu")

@@ -26,7 +26,7 @@ for batch in (1, 2, 4, 8):
     dY = torch.zeros((batch, N), device="cuda")
     alg = sum(plan.traffic(X[b])[0] for b in range(batch))
     n = len(plans)
-    ms = bench.timed_steps(torch, lambda i, cs: plans[i % n].run_batch(dX, dY, cs), 400, 20, st)
+    ms, _ = bench.timed_steps(torch, lambda i, cs: plans[i % n].run_batch(dX, dY, cs), 400, 20, st)
     us = ms * 1e3 / 400
     print(f"{variant} {cfg} batch {batch}: {us:8.3f} us per batched call, {us / batch:7.3f} us per vector, "
           f"{alg / (us * 1e-6) / 1e9:8.1f} GB/s effective", flush=True)
