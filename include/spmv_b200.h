@@ -75,7 +75,8 @@ typedef struct spmv_options {
     int32_t  warps_per_col;  /* wsp: warps cooperating on one column, 1/2/4/8; awsp/tcsr: warps per CTA (0 = auto) */
     int32_t  index_bits;     /* wsp: 16 or 32 bit row indices (0 = auto: 16 if M<65536)  */
     int32_t  slab_cols;      /* awsp/tcsr: columns per slab, power of two 256..4096 (0 = auto from density) */
-    int32_t  chunk_mode;     /* awsp/tcsr: 0 = auto, 1 = one row per 32-group chunk, 2 = short rows packed into shared chunks,
+    int32_t  chunk_mode;     /* awsp/tcsr: 0 = auto (spmv_plan_create_csc: awsp matrices under ~1.2 % density take mode 4),
+                                1 = one row per 32-group chunk, 2 = short rows packed into shared chunks,
                                 3 = lane-owned blocks: for very sparse matrices (segments of a few non-zeros) whose
                                 activations are mostly non-zero — every stored non-zero is read, x is a multiplier,
                                 and a chunk retires in one pass (host packer only; slab_cols 1024..4096, default 2048),

@@ -188,6 +188,19 @@ static int setup_strips(spmv_plan *p, HostStrips &h, const spmv_options_t *o)
 // chunk_mode 4 (row strips) applies to the awsp variant; slab_cols then means columns per strip
 static bool want_strips(const spmv_options_t *o, int variant) { return o && o->chunk_mode == 4 && variant == SPMV_AWSP; }
 
+// chunk_mode auto on the CSR(A^T) route (the route of matrices that cannot exist densely): awsp takes the
+// row-strip form where the row-addressable panel form would fall into its multi-row schedule (segments
+// under 12 groups even at 4096 columns, i.e. under ~1.2 % density) and a strip still holds a useful
+// number of non-zeros per row (>= 8 at the widest strip).  BASELINE config 5 (1 %) is the case in point:
+// 97 us per slab against 160 us.
+static bool auto_strips(const spmv_options_t *o, int variant, int64_t M, int64_t N, int64_t entries)
+{
+    if (variant != SPMV_AWSP || M <= 0 || N <= 0 || entries <= 0) return false;
+    if (o && (o->chunk_mode != 0 || o->slab_cols != 0 || o->row_splits != 0 || o->warps_per_col != 0)) return false;
+    const double density = (double)entries / ((double)M * (double)N);
+    return density * kMaxSlabCols < 48.0 && density * kMaxStripCols >= 8.0 && M >= 1024;
+}
+
 static bool opts_ok(const spmv_options_t *o)
 {
     if (!o) return true;
@@ -436,9 +449,9 @@ int spmv_plan_create_csc(int variant, int64_t M, int64_t N, const int64_t *col_p
             rc = pack_wsp_csc(M, N, col_ptr, row_idx, values, opts ? opts->index_bits : 0, w);
             if (rc) set_error(rc, "wsp: cannot pack (row index out of range, index width or size limits)");
             else rc = setup_wsp(p, w, opts);
-        } else if (want_strips(opts, variant)) {
+        } else if (want_strips(opts, variant) || auto_strips(opts, variant, M, N, col_ptr[N] - col_ptr[0])) {
             HostStrips h;
-            rc = pack_strips_csc(M, N, col_ptr, row_idx, values, opts->slab_cols, h);
+            rc = pack_strips_csc(M, N, col_ptr, row_idx, values, want_strips(opts, variant) ? opts->slab_cols : 0, h);
             if (rc) set_error(rc, "strips: cannot pack (row index out of range, repeated entry, strip width or size limits)");
             else rc = setup_strips(p, h, opts);
         } else {
@@ -898,6 +911,7 @@ int spmv_run_batch(spmv_plan_t *p, int batch, const float *d_X, int64_t ldx, flo
 int spmv_run_scatter(spmv_plan_t *p, const float *d_x, int n_dst, float *const *d_y_dst, float *d_y_multicast,
                      int64_t offset, void *stream)
 {
+
     if (!p) return set_error(SPMV_ERR_ARG, "null plan");
     if (!d_x && p->M > 0) return set_error(SPMV_ERR_ARG, "null device vector");
     if (n_dst < 1 || n_dst > kMaxYDst || !d_y_dst) return set_error(SPMV_ERR_ARG, "1..%d destinations required", kMaxYDst);

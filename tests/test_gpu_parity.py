@@ -735,3 +735,59 @@ def test_row_strips_device_packer_matches_host_packer(S, tmp_path, M, N, density
                                        torch.from_numpy(va).cuda(), chunk_mode=4, **kw)
     with pytest.raises(S.SpmvError):                       # other forms are packed on the host
         S.Plan.from_csc_device("awsp", M, N, torch.from_numpy(cp).cuda(), torch.from_numpy(ri).cuda(), torch.from_numpy(va).cuda())
+
+
+# ---- BASELINE configs 4 and 5 at FULL size, oracle on sampled columns ------------------------------
+def _sampled_oracle(N, cp, ri, va, x, n_cols, seed):
+    """y of `n_cols` seeded columns through the oracle (fp32 sequential csr_naive.cu:14-22 semantics + fp64)."""
+    rng = np.random.default_rng(seed)
+    cols = np.sort(rng.choice(N, size=n_cols, replace=False))
+    lens = (cp[cols + 1] - cp[cols]).astype(np.int64)
+    scp = np.zeros(n_cols + 1, np.int64)
+    np.cumsum(lens, out=scp[1:])
+    take = np.concatenate([np.arange(cp[c], cp[c + 1]) for c in cols])
+    sri, sva = ri[take], va[take]
+    y32 = ob.csc_gemv(n_cols, scp, sri, sva, x)
+    xa = x.astype(np.float64)[sri] * sva.astype(np.float64)
+    seg = np.repeat(np.arange(n_cols), lens)
+    return cols, y32, np.bincount(seg, weights=xa, minlength=n_cols), np.bincount(seg, weights=np.abs(xa), minlength=n_cols)
+
+
+@pytest.mark.gpu
+def test_config5_full_size_slab_against_sampled_oracle(S):
+    """One GPU's slab of BASELINE config 5 exactly as bench.py builds it (65536 x 131072, 1 %, seed 5000, x seed 4321):
+    the host packer, the device packer and the automatic choice of the row-strip form give the same bits, 4096
+    sampled columns are inside the parity gate, two runs are bit-identical."""
+    import torch
+    from spmv_test_b200 import synth
+    M, N = 65536, 131072
+    cp, ri, va = synth.bernoulli_csc(M, N, 0.01, seed=5000)
+    x = synth.gen_vector(M, 0.5, seed=4321)
+    cols, y32, y64, s = _sampled_oracle(N, cp, ri, va, x, 4096, 900)
+    with S.Plan.from_csc_device("awsp", M, N, torch.from_numpy(cp).cuda(), torch.from_numpy(ri).cuda(), torch.from_numpy(va).cuda(),
+                                chunk_mode=4) as pd:
+        y = pd.run_host(x)
+        check_y(y[cols], y32, y64, s, "config 5 slab, row strips (device packer)")
+        assert pd.run_host(x).tobytes() == y.tobytes()
+        info = pd.info()
+        assert info["slab_cols"] == 2048 and info["kernels_per_run"] == 2 and info["nnz"] == int(np.count_nonzero(va))
+        alg, phys, touched = pd.traffic(x)
+        assert touched == int(np.count_nonzero(x[ri] != 0)) and alg == 8.0 * touched + 4.0 * (N + 1) + 4.0 * M + 4.0 * N
+    with S.Plan.from_csc("awsp", M, N, cp, ri, va) as pa:                   # chunk_mode auto -> row strips on this density
+        assert pa.info()["slab_cols"] == 2048 and pa.info()["index_bits"] == 32
+        assert pa.run_host(x).tobytes() == y.tobytes()
+
+
+@pytest.mark.gpu
+def test_config4_full_size_against_sampled_oracle(S):
+    """BASELINE config 4 exactly as bench.py builds it (1M x 1M power-law columns, seed 42, dense x): 4096 sampled
+    columns inside the parity gate, one merged launch, two runs bit-identical."""
+    from spmv_test_b200 import synth
+    M = N = 1 << 20
+    cp, ri, va = synth.powerlaw_csc(M, N, seed=42)
+    x = synth.gen_vector(M, 0.0, seed=7)
+    cols, y32, y64, s = _sampled_oracle(N, cp, ri, va, x, 4096, 404)
+    with S.Plan.from_csc("wsp", M, N, cp, ri, va) as p:
+        y = p.run_host(x)
+        check_y(y[cols], y32, y64, s, "config 4 wsp")
+        assert p.info()["kernels_per_run"] == 1 and p.run_host(x).tobytes() == y.tobytes()
