@@ -563,10 +563,12 @@ int configure_panel(spmv_plan *p, const HostPanel &h, const spmv_options_t *o)
     d.row_blocks = h.row_blocks; d.tiled = h.tiled;
     d.block_rows = h.block_rows; d.lob_blocks = h.lob_blocks;
     const bool lob = h.block_rows > 0;
-    // short segments (fewer than 12 groups on average, i.e. chunks less than 3/8 full): pack
+    // short segments (fewer than 6 groups on average, i.e. chunks less than a fifth full): pack
     // several rows into one chunk
     const double segs = std::max<double>(1.0, (double)h.nonempty_segments);
-    d.multirow = (double)h.groups / segs < 12.0;
+    // (round 2: with the register-staged one-row-per-chunk kernel the crossover moved down — config 1, 6.4 groups
+    // per segment: 9.25 us there against 10.26 us multi-row)
+    d.multirow = (double)h.groups / segs < 6.0;
     if (o && o->chunk_mode == 1) d.multirow = false;
     if (o && o->chunk_mode == 2) d.multirow = true;
     if (lob) d.multirow = false;
