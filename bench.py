@@ -197,7 +197,7 @@ def record_parity(what, fn):
         return "FAILED: " + str(e)[:160]
 
 
-def measure_variant(torch, S, variant, build, x, steps, warmup, stream, check=None, hot=False):
+def measure_variant(torch, S, variant, build, x, steps, warmup, stream, check=None, hot=False, e2e=False):
     """Pack, check against the oracle, clone, time.  `build(variant)` returns a Plan;
     `check(variant, y)` raises AssertionError on a parity failure."""
     t0 = time.perf_counter()
@@ -225,6 +225,17 @@ def measure_variant(torch, S, variant, build, x, steps, warmup, stream, check=No
            "slab_cols": info["slab_cols"], "row_splits": info["row_splits"], "pack_s": round(pack_s, 2)}
     if parity is not None:
         res["parity"] = parity
+    if e2e:                                               # the reference launcher's per-call part: pinned host x in, y out, synchronise
+        hx = torch.from_numpy(x).pin_memory()
+        hy = torch.empty(info["N"], dtype=torch.float32).pin_memory()
+        n_e = max(20, min(steps, 400))
+        for _ in range(5):
+            plan.run_host_ptr(hx.data_ptr(), hy.data_ptr())
+        t0 = time.perf_counter()
+        for _ in range(n_e):
+            plan.run_host_ptr(hx.data_ptr(), hy.data_ptr())
+        res["e2e_us_per_call"] = round((time.perf_counter() - t0) / n_e * 1e6, 2)
+        res["e2e_bytes"] = {"h2d": int(hx.numel() * 4), "d2h": int(hy.numel() * 4)}
     if hot:                                               # the same call on ONE resident copy: L2-warm when it fits
         ms_h, per_h = timed_steps(torch, lambda i, cs: plan.run(dx, dy, cs), steps, warmup, stream, graph=GRAPH)
         res["hot_l2_us_per_call"] = round(ms_h * 1e3 / steps, 3)
@@ -657,9 +668,10 @@ def main():
                           "oracle": "orc_sgemv_dense (tester.cpp:36-45 restated), all columns"}
             for v in ("wsp", "asp", "awsp", "tcsr"):
                 r, pl, _, _ = measure_variant(torch, S, v, lambda vv: S.Plan.from_dense(vv, Ac), xc, v_steps, v_warm, stream,
-                                              check=lambda vv, y: parity.check_y(y, y32, y64, sabs, f"{name} {vv}"), hot=True)
-                keep = ("us_per_call", "us_min", "us_median", "hot_l2_us_per_call", "alg_MB", "phys_MB", "eff_GBps", "phys_GBps",
-                        "l2_copies", "parity", "kernels_per_call")
+                                              check=lambda vv, y: parity.check_y(y, y32, y64, sabs, f"{name} {vv}"), hot=True,
+                                              e2e=(name == "c2"))
+                keep = ("us_per_call", "us_min", "us_median", "hot_l2_us_per_call", "e2e_us_per_call", "e2e_bytes", "alg_MB", "phys_MB",
+                        "eff_GBps", "phys_GBps", "l2_copies", "parity", "kernels_per_call")
                 cfgs[name][v] = {k: r[k] for k in keep if k in r}
                 cfgs[name][v]["frac_alg"] = round(r["eff_GBps"] / peak, 4)
                 cfgs[name][v]["frac_phys"] = round(r["phys_GBps"] / peak, 4)

@@ -195,6 +195,14 @@ wsp_merged_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ id
 // FIFO, independent of register and scoreboard limits), partial chunks are zero-filled,
 // x is gathered from shared memory.  The packer
 // deals each chunk's entries so that the 32 lanes' gathers fall into distinct banks.
+// Round 2 A/Bs of how a chunk reaches the ring (same box, us per call, config 2 / 0 / 3; profiles/r02_notes.md):
+//   cp.async, 16 + 8 bytes per lane (this code)                          22.4 / 13.9 / 22.0
+//   two 1-D bulk async copies per chunk (TMA engine, cp.async.bulk +
+//   one mbarrier per ring slot, issued by lane 0; the patch is kept as
+//   profiles/r02_wsp_bulk_ring_variant.patch)                           30.1 / 17.6 / 33.3   (batch of 4: 85.8 vs 44.6)
+//   chunks in flight in registers (8 x 6 registers, three CTAs per SM)   21.7 / 13.9 / 26.4
+// The bulk engine loses on 768-byte pieces (as it did on 256..1024-byte row segments in round 1's
+// tools/ubench/bulk_vs_ldgsts.cu), and this kernel's LSU work is dominated by the x gathers, not the staging.
 #ifndef SPMV_WSP_STAGES
 #define SPMV_WSP_STAGES 8
 #endif
