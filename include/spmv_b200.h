@@ -306,7 +306,9 @@ SPMV_API int  spmv_mg_connect_ptrs(spmv_mg_t *mg, void *const *blocks /* world *
 SPMV_API int  spmv_mg_add_plan(spmv_mg_t *mg, spmv_plan_t *plan, int64_t col_offset);
 /* asynchronous on `stream`; *d_y = this rank's copy of the full y, complete when the stream reaches this point */
 SPMV_API int  spmv_mg_run(spmv_mg_t *mg, const float *d_x, void *stream, const float **d_y);
-/* H2D x, spmv_mg_run, D2H y[y_begin, y_begin + y_count), synchronise (y_count = 0: no copy back) */
+/* H2D x, spmv_mg_run, D2H y[y_begin, y_begin + y_count), synchronise (y_count = 0: no copy back).  When the range lies inside
+ * this rank's own slabs and there are several of them, each slab's columns travel to the host (second stream, one event per
+ * slab) while the later slabs still compute; pinned host memory makes that overlap real. */
 SPMV_API int  spmv_mg_run_host(spmv_mg_t *mg, const float *x, float *y, int64_t y_begin, int64_t y_count);
 /* SPMV_OK, or SPMV_ERR_CUDA if an arrival wait timed out (a peer died); synchronous */
 SPMV_API int  spmv_mg_status(spmv_mg_t *mg);

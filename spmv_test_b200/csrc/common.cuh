@@ -75,6 +75,7 @@ __device__ __forceinline__ void y_store4(const YDst &d, size_t i4, float4 v)   /
 // programmatic dependent launch (plan.hpp: launch_k): the kernel may have been placed before the
 // previous grid in the stream has flushed; wait for it before touching anything it may have written
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;

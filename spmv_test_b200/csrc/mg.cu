@@ -16,8 +16,10 @@
 // It is either allocated here (cudaMalloc; other processes map it through a CUDA IPC handle,
 // other devices of the same process through peer access) or supplied by the caller (symmetric
 // memory with a multicast alias, e.g. torch.distributed._symmetric_memory).
+#include <algorithm>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -38,6 +40,7 @@ struct MgJoin {
 
 __global__ void __launch_bounds__(32) mg_join_kernel(const MgJoin j)
 {
+    pdl_trigger();                                        // the next call's first kernel may come up and wait behind this one
     pdl_wait();                                           // every kernel of this call has finished and flushed
     const int t = threadIdx.x;
     unsigned e = 0;
@@ -77,6 +80,8 @@ struct spmv_mg {
     unsigned *epoch = nullptr, *status = nullptr;
     float *d_x = nullptr;                     // staging for run_host
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;       // run_host: a slab's columns travel to the host while the next slab computes
+    std::vector<cudaEvent_t> part_done;       // one per part, recorded on `stream` behind the part's kernels
     uint64_t calls = 0;                       // host mirror of the epoch (picks the y buffer)
     struct Part { spmv_plan *plan; int64_t off; };
     std::vector<Part> parts;
@@ -113,6 +118,7 @@ int spmv_mg_create(int64_t M, int64_t N_total, int rank, int world, void *local_
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&g->d_x), ((size_t)M + 4) * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(g->d_x, 0, ((size_t)M + 4) * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return fail(cuda_error(e, "spmv_mg_create"));
     g->status = g->epoch + 1;
@@ -132,6 +138,8 @@ void spmv_mg_destroy(spmv_mg_t *g)
     if (g->epoch) cudaFree(g->epoch);
     if (g->d_x) cudaFree(g->d_x);
     if (g->stream) cudaStreamDestroy(g->stream);
+    if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
+    for (cudaEvent_t e : g->part_done) cudaEventDestroy(e);
     cudaGetLastError();
     delete g;
 }
@@ -189,7 +197,10 @@ int spmv_mg_add_plan(spmv_mg_t *g, spmv_plan_t *plan, int64_t col_offset)
     return SPMV_OK;
 }
 
-int spmv_mg_run(spmv_mg_t *g, const float *d_x, void *stream, const float **d_y)
+} // extern "C"
+
+// the step; with `mark` an event is recorded on the stream behind every part's kernels (run_host's copy-back pipeline)
+static int mg_run_step(spmv_mg *g, const float *d_x, void *stream, const float **d_y, bool mark)
 {
     if (!g) return set_error(SPMV_ERR_ARG, "null group");
     if (!g->connected) return set_error(SPMV_ERR_ARG, "spmv_mg_run before the ranks were connected");
@@ -203,6 +214,7 @@ int spmv_mg_run(spmv_mg_t *g, const float *d_x, void *stream, const float **d_y)
         // own rank first is not required: the epilogue stores to every destination alike
         int rc = spmv_run_scatter(pt.plan, d_x, g->world, dst, mc, pt.off, st);
         if (rc) return rc;
+        if (mark) SPMV_CUDA(cudaEventRecord(g->part_done[(size_t)(&pt - g->parts.data())], st));
     }
     if (g->world > 1) {
         MgJoin j{};
@@ -216,6 +228,52 @@ int spmv_mg_run(spmv_mg_t *g, const float *d_x, void *stream, const float **d_y)
     g->calls++;
     return SPMV_OK;
 }
+
+// Copy-back of run_host.  A part's own columns of y are final in this rank's block as soon as the part's
+// kernels have run (the arrival only concerns the peers' columns), so when the requested range lies inside
+// this rank's parts each part's columns leave on the copy stream behind the part's event while the later
+// parts still compute; otherwise one copy behind the whole step.  Nothing is synchronised here.
+static int mg_copy_back(spmv_mg *g, const float *dy, float *y, int64_t y_begin, int64_t y_count, bool marked)
+{
+    if (y_count <= 0) return SPMV_OK;
+    if (!marked) {
+        SPMV_CUDA(cudaMemcpyAsync(y, dy + y_begin, (size_t)y_count * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+        return SPMV_OK;
+    }
+    for (size_t k = 0; k < g->parts.size(); k++) {
+        const spmv_mg::Part &pt = g->parts[k];
+        const int64_t a = std::max(y_begin, pt.off), b = std::min(y_begin + y_count, pt.off + pt.plan->N);
+        if (b <= a) continue;
+        SPMV_CUDA(cudaStreamWaitEvent(g->copy_stream, g->part_done[k], 0));
+        SPMV_CUDA(cudaMemcpyAsync(y + (a - y_begin), dy + a, (size_t)(b - a) * sizeof(float), cudaMemcpyDeviceToHost, g->copy_stream));
+    }
+    return SPMV_OK;
+}
+
+// true when [y_begin, y_begin + y_count) is covered by this rank's parts (several of them: otherwise nothing overlaps)
+static bool mg_can_pipeline(spmv_mg *g, int64_t y_begin, int64_t y_count)
+{
+    if (y_count <= 0 || g->parts.size() < 2) return false;
+    std::vector<std::pair<int64_t, int64_t>> iv;
+    for (const spmv_mg::Part &pt : g->parts) iv.push_back({pt.off, pt.off + pt.plan->N});
+    std::sort(iv.begin(), iv.end());
+    int64_t reach = y_begin;
+    for (const auto &r : iv) {
+        if (r.first > reach) break;
+        reach = std::max(reach, r.second);
+    }
+    if (reach < y_begin + y_count) return false;
+    while (g->part_done.size() < g->parts.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+        g->part_done.push_back(e);
+    }
+    return true;
+}
+
+extern "C" {
+
+int spmv_mg_run(spmv_mg_t *g, const float *d_x, void *stream, const float **d_y) { return mg_run_step(g, d_x, stream, d_y, false); }
 
 int spmv_mg_status(spmv_mg_t *g)
 {
@@ -233,10 +291,13 @@ int spmv_mg_run_host(spmv_mg_t *g, const float *x, float *y, int64_t y_begin, in
     if (y_begin < 0 || y_count < 0 || y_begin + y_count > g->N) return set_error(SPMV_ERR_ARG, "y range outside [0, N)");
     if (g->M > 0) SPMV_CUDA(cudaMemcpyAsync(g->d_x, x, (size_t)g->M * sizeof(float), cudaMemcpyHostToDevice, g->stream));
     const float *dy = nullptr;
-    int rc = spmv_mg_run(g, g->d_x, g->stream, &dy);
+    const bool pipe = mg_can_pipeline(g, y_begin, y_count);
+    int rc = mg_run_step(g, g->d_x, g->stream, &dy, pipe);
+    if (!rc) rc = mg_copy_back(g, dy, y, y_begin, y_count, pipe);
+    const cudaError_t e1 = cudaStreamSynchronize(g->stream), e2 = pipe ? cudaStreamSynchronize(g->copy_stream) : cudaSuccess;
     if (rc) return rc;
-    if (y_count > 0) SPMV_CUDA(cudaMemcpyAsync(y, dy + y_begin, (size_t)y_count * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
-    SPMV_CUDA(cudaStreamSynchronize(g->stream));
+    if (e1 != cudaSuccess) return cuda_error(e1, "cudaStreamSynchronize");
+    if (e2 != cudaSuccess) return cuda_error(e2, "cudaStreamSynchronize(copy stream)");
     return SPMV_OK;
 }
 
@@ -303,22 +364,34 @@ extern "C" int spmv_mg_group_run_host(spmv_mg_t *const *groups, int n_dev, const
         if (g->M > 0 && cudaMemcpyAsync(g->d_x, x, (size_t)g->M * sizeof(float), cudaMemcpyHostToDevice, g->stream) != cudaSuccess)
             rc = cuda_error(cudaGetLastError(), "cudaMemcpyAsync(x)");
     }
+    std::vector<char> pipe((size_t)n_dev, 0);
     for (int i = 0; i < n_dev && !rc; i++) {
-        cudaSetDevice(groups[i]->device);
-        rc = spmv_mg_run(groups[i], groups[i]->d_x, groups[i]->stream, &dy[(size_t)i]);
+        spmv_mg *g = groups[i];
+        cudaSetDevice(g->device);
+        // every part's columns are wanted, so the pipeline condition is just "several parts" (events are made here)
+        pipe[(size_t)i] = g->parts.size() > 1 && mg_can_pipeline(g, g->parts[0].off, 1);
+        rc = mg_run_step(g, g->d_x, g->stream, &dy[(size_t)i], pipe[(size_t)i] != 0);
     }
     for (int i = 0; i < n_dev && !rc; i++) {                // own columns only: the union over the devices is all of y
         spmv_mg *g = groups[i];
         cudaSetDevice(g->device);
-        for (const spmv_mg::Part &pt : g->parts)
-            if (pt.plan->N > 0 && cudaMemcpyAsync(y + pt.off, dy[(size_t)i] + pt.off, (size_t)pt.plan->N * sizeof(float),
-                                                  cudaMemcpyDeviceToHost, g->stream) != cudaSuccess)
+        for (size_t k = 0; k < g->parts.size() && !rc; k++) {
+            const spmv_mg::Part &pt = g->parts[k];
+            if (pt.plan->N <= 0) continue;
+            cudaStream_t cs = g->stream;
+            if (pipe[(size_t)i]) {
+                cs = g->copy_stream;
+                if (cudaStreamWaitEvent(cs, g->part_done[k], 0) != cudaSuccess) { rc = cuda_error(cudaGetLastError(), "cudaStreamWaitEvent"); break; }
+            }
+            if (cudaMemcpyAsync(y + pt.off, dy[(size_t)i] + pt.off, (size_t)pt.plan->N * sizeof(float), cudaMemcpyDeviceToHost, cs) != cudaSuccess)
                 rc = cuda_error(cudaGetLastError(), "cudaMemcpyAsync(y)");
+        }
     }
     for (int i = 0; i < n_dev; i++) {
         if (!groups[i]) continue;
         cudaSetDevice(groups[i]->device);
-        const cudaError_t e = cudaStreamSynchronize(groups[i]->stream);
+        cudaError_t e = cudaStreamSynchronize(groups[i]->stream);
+        if (e == cudaSuccess && pipe[(size_t)i]) e = cudaStreamSynchronize(groups[i]->copy_stream);
         if (e != cudaSuccess && !rc) rc = cuda_error(e, "cudaStreamSynchronize");
         if (!rc) rc = spmv_mg_status(groups[i]);
     }

@@ -43,6 +43,18 @@ constexpr int kRsBatch = SPMV_RS_BATCH;       // 32-row blocks scanned per list 
 #ifndef SPMV_RS_CTAS
 #define SPMV_RS_CTAS 2
 #endif
+// Bit 0: the reduce kernel releases its dependents at entry, and a CTA of the main kernel fetches the static
+// metadata (segment offsets) of its first blocks BEFORE the grid dependency wait — so across back-to-back
+// calls the next call's CTAs are resident, zeroed and one memory round trip ahead while the previous call's
+// partial rows are still being summed.  Bit 1: the main kernel also releases the reduce kernel after its
+// streaming loop.  Same-box A/B, us per call, awsp c2 / c0 / c1 / c3 then tcsr: off 16.56 11.62 8.92 9.78 |
+// 17.62 12.81 10.10 10.23; bit 0: 16.06 11.31 8.56 9.41 | 16.98 11.69 9.32 9.32; bit 1: 17.06 11.98 9.08
+// 10.06 | 18.06 13.15 10.22 10.47; both: 16.64 11.81 9.02 9.98 | 16.99 11.87 9.28 9.71.  Bit 0 it is.
+#ifndef SPMV_RS_EARLY
+#define SPMV_RS_EARLY 1
+#endif
+constexpr bool kRsEarly = (SPMV_RS_EARLY & 1) != 0;        // reduce kernel releases at entry, main kernel prefetches before its wait
+constexpr bool kRsTrigger = (SPMV_RS_EARLY & 2) != 0;      // main kernel releases the reduce kernel after its streaming loop
 constexpr int kRsCtas = SPMV_RS_CTAS;         // CTAs per SM the register budget is cut for (2: up to 128 registers per thread)
 // rows a warp can get from one list refill: whole blocks when it owns them (BB), else its rank-interleaved share
 __host__ __device__ constexpr int rs_list_rows(bool bb) { return bb ? kRsBatch * 32 : kRsBatch * 32 / kRsWarps; }
@@ -85,8 +97,16 @@ __device__ __forceinline__ float4 rs_load_vals(const float4 *p, bool ok)
 __host__ __device__ constexpr int rs_warp_bytes(int W, bool bb) { return W * 4 + rs_list_rows(bb) * 16; }
 
 // the flat (slab, row) sequence of T = slabs * M units cut into G equal ranges (as in panel.cu)
-__device__ __forceinline__ long long rs_begin(long long c, long long T, long long G) { return c * T / G; }
-__device__ __forceinline__ long long rs_owner(long long u, long long T, long long G) { return ((u + 1) * G - 1) / T; }
+// (`small`: T * G fits 31 bits — every shape but the very largest — so the divisions are 32-bit ones; a 64-bit
+// division is ~100 instructions and the reduce kernel has three of them on its critical path)
+__device__ __forceinline__ long long rs_begin(long long c, long long T, long long G, bool small)
+{
+    return small ? (long long)((unsigned)c * (unsigned)T / (unsigned)G) : c * T / G;
+}
+__device__ __forceinline__ long long rs_owner(long long u, long long T, long long G, bool small)
+{
+    return small ? (long long)((((unsigned)u + 1u) * (unsigned)G - 1u) / (unsigned)T) : ((u + 1) * G - 1) / T;
+}
 
 // BB: the plan's pieces hold at least one 32-row block per warp, so a warp owns whole blocks (compiled as a
 // separate instance: with the larger list and the ownership test in the code the short-piece case ran
@@ -95,7 +115,7 @@ template <int IDXB, bool TILED, bool BB>
 __global__ void __launch_bounds__(kRsThreads, kRsCtas)
 panel_rs_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx, const uint32_t *__restrict__ off,
                 const uint16_t *__restrict__ rel, const float *__restrict__ x, float *__restrict__ partial,
-                int M, int N, int W, int row_blocks, int slabs, int kmax)
+                int M, int N, int W, int row_blocks, int slabs, int kmax, int small)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using IX = RsIdx<IDXB>;
@@ -105,9 +125,13 @@ panel_rs_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx, c
     float *acc = reinterpret_cast<float *>(smem_raw + (size_t)warp * rs_warp_bytes(W, BB));
     uint4 *list = reinterpret_cast<uint4 *>(acc + W);     // (first group, end group, x bits, -) of this warp's rows
 
-    pdl_wait();
+    const int wg = blockIdx.x * kRsWarps + warp;          // (timeline builds only)
+    SPMV_STAMP(wg, 0);
+    SPMV_STAMP_SMID(wg, 8);
+    if (!kRsEarly) pdl_wait();
+    if (!kRsEarly) SPMV_STAMP(wg, 1);
     const long long T = (long long)slabs * M, G = gridDim.x;
-    const long long u_begin = rs_begin(blockIdx.x, T, G), u_end = rs_begin(blockIdx.x + 1, T, G);
+    const long long u_begin = rs_begin(blockIdx.x, T, G, small), u_end = rs_begin(blockIdx.x + 1, T, G, small);
 
     // the chunks in flight: values, column ids, the row's x, valid lanes (0: empty slot)
     float4 sv[kRsDepth]; IVec si[kRsDepth]; float sx[kRsDepth]; int sn[kRsDepth];
@@ -128,7 +152,7 @@ panel_rs_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx, c
 
     int piece = 0;
     for (long long u = u_begin; u < u_end; piece++) {
-        const int slab = (int)(u / M);
+        const int slab = small ? (int)((unsigned)u / (unsigned)M) : (int)(u / M);
         const int row_a = (int)(u - (long long)slab * M);
         const int row_b = (int)min((long long)M, row_a + (u_end - u));
         u += row_b - row_a;
@@ -142,14 +166,16 @@ panel_rs_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx, c
         // issued as soon as this batch's registers have been turned into the list, so their latency overlaps the
         // streaming of this batch's chunks
         float mx[kRsBatch]; uint32_t mg0[kRsBatch], mg1[kRsBatch];
-        auto load_meta = [&](int blk0) {
+        auto load_meta = [&](int blk0, bool statics = true, bool xs = true) {
             const int bstep_ = BB && (blk_b - blk_a) >= kRsWarps ? kRsWarps : 1;
 #pragma unroll
             for (int j = 0; j < kRsBatch; j++) {
                 const int rb = blk0 + j * bstep_, row = rb * 32 + lane;
-                mx[j] = 0.0f; mg0[j] = 0u; mg1[j] = 0u;
+                if (xs) mx[j] = 0.0f;
+                if (statics) { mg0[j] = 0u; mg1[j] = 0u; }
                 if (rb < blk_b && row < M) {
-                    mx[j] = __ldg(x + row);
+                    if (xs) mx[j] = __ldg(x + row);
+                    if (!statics) continue;
                     if (TILED) {
                         const size_t t = (size_t)slab * (row_blocks + 1) + rb;
                         const uint32_t tb = __ldg(off + t), te = __ldg(off + t + 1);
@@ -170,7 +196,12 @@ panel_rs_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx, c
         // active rows whose rank is its own modulo the warp count (exact balance).
         const bool by_block = BB && (blk_b - blk_a) >= kRsWarps;
         const int bstep = by_block ? kRsWarps : 1;
-        load_meta(blk_a + (by_block ? warp : 0));
+        if (kRsEarly && piece == 0) {                     // x (and the partial rows) may belong to the previous kernel: wait first
+            load_meta(blk_a + (by_block ? warp : 0), true, false);
+            pdl_wait();
+            SPMV_STAMP(wg, 1);
+            load_meta(blk_a + (by_block ? warp : 0), false, true);
+        } else load_meta(blk_a + (by_block ? warp : 0));
         for (int blk0 = blk_a + (by_block ? warp : 0); blk0 < blk_b; blk0 += kRsBatch * bstep) {
             // ---- this warp's share of the active rows ----------------------------------------------------
             __syncwarp();                                 // the previous list has been issued completely
@@ -189,6 +220,7 @@ panel_rs_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx, c
             }
             if (blk0 + kRsBatch * bstep < blk_b) load_meta(blk0 + kRsBatch * bstep);
             __syncwarp();
+            if (piece == 0 && blk0 == blk_a + (by_block ? warp : 0)) SPMV_STAMP(wg, 2);
             // ---- the rows' chunks through the register pipeline (it keeps running across refills) -------
             int r = 0;
             uint32_t g = 0u, g1 = 0u;
@@ -212,25 +244,34 @@ panel_rs_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx, c
                         }
                     } else sn[k] = 0;
                 }
+                if (piece == 0 && r <= kRsDepth + 1 && blk0 == blk_a + (by_block ? warp : 0)) SPMV_STAMP(wg, 3);   // (roughly: the first slots have landed)
             }
         }
+        SPMV_STAMP(wg, 4);
+        if (kRsTrigger && u >= u_end) pdl_trigger();        // the reduce kernel's CTAs may take their places (they wait for this grid to finish)
         // ---- end of the piece: drain, then the fixed-order sum of the warps -> one partial row ------------
 #pragma unroll
         for (int k = 0; k < kRsDepth; k++) { consume(sv[k], si[k], sx[k], sn[k]); sn[k] = 0; }
+        SPMV_STAMP(wg, 5);
         __syncthreads();
+        SPMV_STAMP(wg, 6);
         const int n_valid = min(W, N - slab * W);
         const int wstride = rs_warp_bytes(W, BB) / 4;
         const float *acc0 = reinterpret_cast<const float *>(smem_raw);
         float *dst = partial + ((size_t)blockIdx.x * kmax + piece) * W;
-        for (int c = tid; c < W; c += kRsThreads) {
-            float s = 0.0f;
-            if (c < n_valid) {
-                s = acc0[c];
+        for (int c = tid * 4; c < W; c += kRsThreads * 4) {       // (W is a multiple of 4; the warps' rows are 16-byte aligned)
+            float4 s = *reinterpret_cast<const float4 *>(acc0 + c);
 #pragma unroll
-                for (int w = 1; w < kRsWarps; w++) s += acc0[(size_t)w * wstride + c];
+            for (int w = 1; w < kRsWarps; w++) s = f4_add(s, *reinterpret_cast<const float4 *>(acc0 + (size_t)w * wstride + c));
+            if (c + 3 >= n_valid) {                                 // columns past N hold whatever the pads added: zero them
+                if (c >= n_valid) s.x = 0.0f;
+                if (c + 1 >= n_valid) s.y = 0.0f;
+                if (c + 2 >= n_valid) s.z = 0.0f;
+                s.w = 0.0f;
             }
-            dst[c] = s;
+            *reinterpret_cast<float4 *>(dst + c) = s;
         }
+        SPMV_STAMP(wg, 7);
         __syncthreads();                                  // the accumulators are zeroed again by the next piece
     }
 }
@@ -239,15 +280,19 @@ panel_rs_kernel(const float4 *__restrict__ vals, const void *__restrict__ idx, c
 // slab with 8 row groups: group k adds rows k, k+8, ... (8 loads in flight), then the 8 group sums are
 // added in group order: the order depends only on (shape, G).
 __global__ void __launch_bounds__(256)
-panel_rs_reduce_kernel(const float *__restrict__ partial, const YDst yd, int M, int N, int W, int slabs, int kmax, long long G)
+panel_rs_reduce_kernel(const float *__restrict__ partial, const YDst yd, int M, int N, int W, int slabs, int kmax, long long G, int small)
 {
     __shared__ float4 sums[256];
+    const int wg = 32768 + blockIdx.x * 8 + (threadIdx.x >> 5);   // (timeline builds only)
+    SPMV_STAMP(wg, 0);
+    if (kRsEarly) pdl_trigger();
     pdl_wait();
+    SPMV_STAMP(wg, 1);
     const int v = threadIdx.x & 31, k = threadIdx.x >> 5;
     const int per_slab = W / 128;                         // CTAs per slab (W is a power of two >= 256)
     const int slab = blockIdx.x / per_slab, col4 = (blockIdx.x - slab * per_slab) * 32 + v;
     const long long T = (long long)slabs * M;
-    const long long c_lo = rs_owner((long long)slab * M, T, G), c_hi = rs_owner((long long)slab * M + M - 1, T, G);
+    const long long c_lo = rs_owner((long long)slab * M, T, G, small), c_hi = rs_owner((long long)slab * M + M - 1, T, G, small);
     const int rows = (int)(c_hi - c_lo + 1);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = k; j < rows; j += 8 * kRedBatch) {
@@ -258,7 +303,8 @@ panel_rs_reduce_kernel(const float *__restrict__ partial, const YDst yd, int M, 
             t[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (jq < rows) {
                 const long long c = c_lo + jq;
-                const size_t row = (size_t)c * kmax + (size_t)(slab - (int)(rs_begin(c, T, G) / M));
+                const long long cb = rs_begin(c, T, G, small);
+                const size_t row = (size_t)c * kmax + (size_t)(slab - (small ? (int)((unsigned)cb / (unsigned)M) : (int)(cb / M)));
                 t[q] = __ldcg(reinterpret_cast<const float4 *>(partial + row * W) + col4);
             }
         }
@@ -273,12 +319,14 @@ panel_rs_reduce_kernel(const float *__restrict__ partial, const YDst yd, int M, 
         for (int g = 1; g < 8; g++) s = f4_add(s, sums[g * 32 + v]);
         y_store4(yd, ((size_t)slab * W >> 2) + col4, s);
     }
+    SPMV_STAMP(wg, 2);
 }
 
 template <int IDXB, bool TILED, bool BB>
 int launch_rs(spmv_plan *p, const float *x, const YDst &y, cudaStream_t st)
 {
     const DevPanel &d = p->panel;
+    const int small = ((long long)d.slabs * p->M + 1) * ((long long)d.rs_grid + 1) < (1ll << 31) ? 1 : 0;
     auto k = panel_rs_kernel<IDXB, TILED, BB>;
     static int smem_set[16] = {0};
     if (d.rs_smem > 48 * 1024 && p->device >= 0 && p->device < 16 && smem_set[p->device] < d.rs_smem) {
@@ -287,9 +335,9 @@ int launch_rs(spmv_plan *p, const float *x, const YDst &y, cudaStream_t st)
     }
     SPMV_CUDA(launch_k(k, dim3((unsigned)d.rs_grid), dim3(kRsThreads), (size_t)d.rs_smem, st, reinterpret_cast<const float4 *>(d.vals),
                        (const void *)d.idx, (const uint32_t *)d.off, (const uint16_t *)d.rel, x, d.rs_partial, (int)p->M, (int)p->N,
-                       d.slab_cols, d.row_blocks, d.slabs, d.rs_kmax));
+                       d.slab_cols, d.row_blocks, d.slabs, d.rs_kmax, small));
     SPMV_CUDA(launch_k(panel_rs_reduce_kernel, dim3((unsigned)(d.slabs * (d.slab_cols / 128))), dim3(256), 0, st,
-                       (const float *)d.rs_partial, y, (int)p->M, (int)p->N, d.slab_cols, d.slabs, d.rs_kmax, (long long)d.rs_grid));
+                       (const float *)d.rs_partial, y, (int)p->M, (int)p->N, d.slab_cols, d.slabs, d.rs_kmax, (long long)d.rs_grid, small));
     return SPMV_OK;
 }
 

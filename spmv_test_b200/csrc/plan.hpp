@@ -22,9 +22,13 @@ int cuda_error(cudaError_t e, const char *what); // SPMV_ERR_CUDA + message (nev
 
 // Programmatic dependent launch.  Every SGEMV kernel is launched with the programmatic stream
 // serialization attribute and executes `griddepcontrol.wait` (common.cuh: pdl_wait) before it reads
-// or writes global memory.  No kernel triggers its dependents early, so the next kernel of a stream
-// (or captured graph) is placed when the previous grid's CTAs have all exited, and its launch and
-// set-up overlap the previous grid's memory flush; after the wait, ordinary stream order holds.
+// or writes global memory that another kernel of the stream may touch (static plan data may be read
+// or prefetched before it).  The streaming kernels do not trigger their dependents early, so the next
+// kernel of a stream (or captured graph) is placed when the previous grid's CTAs have all exited, and its
+// launch and set-up overlap the previous grid's memory flush; after the wait, ordinary stream order holds.
+// The short tail kernels (panel_rs_reduce_kernel, strips_reduce_kernel, mg_join_kernel) DO release their
+// dependents at entry (pdl_trigger): the next call's first kernel becomes resident, zeroes its accumulators
+// and fetches static metadata while the tail kernel runs, then waits for it.
 // Measured on one box, graph replays: wsp c2 23.03 -> 22.42 us, awsp c2 20.53 -> 20.01, asp c2
 // 24.49 -> 23.99, tcsr c3 11.22 -> 10.66.  An early trigger (griddepcontrol.launch_dependents at
 // kernel entry) lets the next grid's CTAs take free slots next to the running ones and unbalances

@@ -101,8 +101,16 @@ strips_kernel(const uint2 *__restrict__ ent, const uint32_t *__restrict__ soff, 
     const unsigned lt = (1u << lane) - 1u;
 
     for (int c = lane; c < sw + 32; c += 32) acc[c] = 0.0f;
-    pdl_wait();
     const uint32_t *so = soff + ((size_t)band * (kStripsPerBand + 1) + warp) * M;   // strip-major: this strip's starts, row by row
+    // The reduce kernel of the previous call releases its dependents at entry, so this CTA is usually resident
+    // and zeroed before that call has finished: the offset records of its first rows (static plan data) are
+    // pulled into L2 meanwhile; x and the partial rows may belong to the previous kernels and wait.
+    for (int r = lane * 32; r < min(row_b - row_a, kStripSub) + 32; r += 32 * 32) {
+        const int row = min(row_a + r, M - 1);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(so + row));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(so + M + row));
+    }
+    pdl_wait();
     uint64_t ent_lane = reinterpret_cast<uint64_t>(ent + lane);   // opaque to the optimiser: one IMAD.WIDE per address
     asm volatile("" : "+l"(ent_lane));
     const uint32_t ring_lane = smem_u32(ring + lane);
@@ -295,6 +303,7 @@ __global__ void __launch_bounds__(256)
 strips_reduce_kernel(const float *__restrict__ partial, const YDst yd, int N, int band_cols, int R)
 {
     __shared__ float4 sums[256];
+    pdl_trigger();                                        // the next kernel's CTAs may come up (and wait) while this one runs
     pdl_wait();
     const int v = threadIdx.x & 31, k = threadIdx.x >> 5;
     const size_t i4 = (size_t)blockIdx.x * 32 + v;
