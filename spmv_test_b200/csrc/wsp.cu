@@ -14,6 +14,7 @@
 // cross-warp sum.  No atomics.
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -25,6 +26,10 @@ namespace {
 
 constexpr int kWspBlock = 256;
 constexpr int kWspUnroll = 4;
+#ifndef SPMV_WSP_MERGED_CTAS
+#define SPMV_WSP_MERGED_CTAS 4
+#endif
+constexpr int kWspMergedCtas = SPMV_WSP_MERGED_CTAS;      // resident CTAs per SM of the L2-gather kernels (register budget and bin grids)
 
 template <typename IdxVec> struct IdxTraits;
 template <> struct IdxTraits<uint2> {   // 4 x u16
@@ -144,6 +149,80 @@ wsp_body(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
     }
 }
 
+// Short columns of a skewed matrix with x gathered through L2 (BASELINE config 4: a 4-thread team, one
+// group per thread, mean 16 non-zeros per column).  One column per team at a time is a chain of four
+// dependent memory round trips (bin list -> column range -> values / row ids -> x) with one load per
+// thread in flight at each step: ncu showed 74 % of the stall samples on the long scoreboard at 45 %
+// occupancy (profiles/r02_ncu_c4_wsp_merged.txt).  Here a team takes C columns at once and issues each
+// step's loads for all of them before it uses any.  Per column the arithmetic and its order are those of
+// wsp_body (same per-thread group sequence, same 4 chains, same shuffle tree): bit-identical results.
+// Same-box A/B on config 4, us per call (resident CTAs per SM x columns per team; bin grids of 4 / 8 / 16 CTAs per
+// SM): 8 x 1 (round 1) 102.4 / 107.0 / 112.9; 4 x 2 94.1 / 98.2 / 102.9; 6 x 2 100.5 / 104.9 / 111.6; 3 x 4 121.3 /
+// 107.4 / 124.3; 2 x 8 141.4 / 157.9 / 173.9.  Two columns at a time with half the threads is the optimum: beyond
+// that the gathers are limited by the L2 sector rate (16 M sectors for 16 M useful words), not by latency.
+#ifndef SPMV_WSP_SHORT_COLS
+#define SPMV_WSP_SHORT_COLS 2
+#endif
+template <typename IdxVec, int T, int C>
+__device__ __forceinline__ void
+wsp_body_short(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx, const uint32_t *__restrict__ colptr,
+               const int32_t *__restrict__ cols, int ncols, const float *__restrict__ x, const YDst &yd, uint32_t M,
+               int bid, int nblocks)
+{
+    static_assert(T <= 32, "a team is part of one warp");
+    constexpr int kTeams = kWspBlock / T;
+    const int tid = threadIdx.x, tl = tid % T;
+    const int team = bid * kTeams + tid / T, nteams = nblocks * kTeams;
+    for (int k0 = team * C; k0 < ncols; k0 += nteams * C) {
+        int c[C];
+        uint32_t g0[C], g1[C];
+#pragma unroll
+        for (int j = 0; j < C; j++) c[j] = k0 + j < ncols ? (cols ? __ldg(cols + k0 + j) : k0 + j) : -1;
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            g0[j] = 0u; g1[j] = 0u;
+            if (c[j] >= 0) { g0[j] = __ldg(colptr + c[j]); g1[j] = __ldg(colptr + c[j] + 1); }
+        }
+        float4 v[C];
+        IdxVec iv[C];
+#pragma unroll
+        for (int j = 0; j < C; j++) {                       // every column's first group of this thread
+            const uint32_t gg = g0[j] + tl;
+            if (gg < g1[j]) { v[j] = ldg_stream_f4(vals + gg); iv[j] = IdxTraits<IdxVec>::load(idx + gg); }
+            else { v[j] = make_float4(0.f, 0.f, 0.f, 0.f); iv[j] = IdxTraits<IdxVec>::pad(0u); }
+        }
+        float xg[C][4];
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            uint32_t i[4];
+            IdxTraits<IdxVec>::unpack(iv[j], i);
+#pragma unroll
+            for (int q = 0; q < 4; q++) xg[j][q] = i[q] < M ? __ldg(x + i[q]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            float a0 = fmaf(v[j].x, xg[j][0], 0.f), a1 = fmaf(v[j].y, xg[j][1], 0.f);
+            float a2 = fmaf(v[j].z, xg[j][2], 0.f), a3 = fmaf(v[j].w, xg[j][3], 0.f);
+            for (uint32_t g = g0[j] + tl + T; g < g1[j]; g += T) {   // (columns of this bin hold at most 8 T groups)
+                const float4 vv = ldg_stream_f4(vals + g);
+                uint32_t i[4];
+                IdxTraits<IdxVec>::unpack(IdxTraits<IdxVec>::load(idx + g), i);
+                const float x0 = i[0] < M ? __ldg(x + i[0]) : 0.f, x1 = i[1] < M ? __ldg(x + i[1]) : 0.f;
+                const float x2 = i[2] < M ? __ldg(x + i[2]) : 0.f, x3 = i[3] < M ? __ldg(x + i[3]) : 0.f;
+                a0 = fmaf(vv.x, x0, a0); a1 = fmaf(vv.y, x1, a1); a2 = fmaf(vv.z, x2, a2); a3 = fmaf(vv.w, x3, a3);
+            }
+            float acc = (a0 + a1) + (a2 + a3);
+            if (T == 32) {
+                acc = warp_sum(acc);
+            } else {
+#pragma unroll
+                for (int sft = T / 2; sft >= 1; sft >>= 1) acc += __shfl_xor_sync(kFull, acc, sft);
+            }
+            if (tl == 0 && c[j] >= 0) y_store(yd, c[j], acc);
+        }
+    }
+}
+
 template <typename IdxVec, int T, bool XS>
 __global__ void __launch_bounds__(kWspBlock)
 wsp_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
@@ -167,7 +246,7 @@ struct BinTable {
 };
 
 template <typename IdxVec>
-__global__ void __launch_bounds__(kWspBlock)
+__global__ void __launch_bounds__(kWspBlock, SPMV_WSP_MERGED_CTAS)
 wsp_merged_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
                   const uint32_t *__restrict__ colptr, const BinTable tb, const float *__restrict__ x,
                   const YDst yd, uint32_t M)
@@ -179,9 +258,9 @@ wsp_merged_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ id
     const int32_t *cols = tb.cols[b];
     const int ncols = tb.ncols[b];
     switch (tb.T[b]) {
-    case 4: wsp_body<IdxVec, 4, false>(vals, idx, colptr, cols, ncols, x, yd, M, 0, bid, nb); break;
-    case 8: wsp_body<IdxVec, 8, false>(vals, idx, colptr, cols, ncols, x, yd, M, 0, bid, nb); break;
-    case 16: wsp_body<IdxVec, 16, false>(vals, idx, colptr, cols, ncols, x, yd, M, 0, bid, nb); break;
+    case 4: wsp_body_short<IdxVec, 4, SPMV_WSP_SHORT_COLS>(vals, idx, colptr, cols, ncols, x, yd, M, bid, nb); break;
+    case 8: wsp_body_short<IdxVec, 8, SPMV_WSP_SHORT_COLS>(vals, idx, colptr, cols, ncols, x, yd, M, bid, nb); break;
+    case 16: wsp_body_short<IdxVec, 16, 2>(vals, idx, colptr, cols, ncols, x, yd, M, bid, nb); break;
     case 32: wsp_body<IdxVec, 32, false>(vals, idx, colptr, cols, ncols, x, yd, M, 0, bid, nb); break;
     case 64: wsp_body<IdxVec, 64, false>(vals, idx, colptr, cols, ncols, x, yd, M, 0, bid, nb); break;
     case 128: wsp_body<IdxVec, 128, false>(vals, idx, colptr, cols, ncols, x, yd, M, 0, bid, nb); break;
@@ -550,7 +629,9 @@ int configure_wsp(spmv_plan *p, const HostWsp &w, const spmv_options_t *o)
         bins.swap(keep);
     }
     // occupancy-sized persistent grids
-    const int ctas_per_sm = p->wsp.x_in_smem ? std::max(1, std::min(8, (int)((200 * 1024) / std::max(p->smem, 1)))) : 8;
+    const bool merged = !p->wsp.x_in_smem && bins.size() > 1 && (int)bins.size() <= kMaxBins;   // (launch_wsp's condition)
+    int ctas_per_sm = p->wsp.x_in_smem ? std::max(1, std::min(8, (int)((200 * 1024) / std::max(p->smem, 1)))) : merged ? kWspMergedCtas : 8;
+    if (const char *e = std::getenv("SPMV_WSP_BIN_CTAS")) ctas_per_sm = std::max(1, std::atoi(e));   // development knob
     for (Bin &b : bins) {
         WspBinDev d{};
         d.T = b.T;
