@@ -8,9 +8,10 @@
 //     shared-memory list of (row, x[row]) with x[row] != 0.0f (asp.cu:23's test, made a pass:
 //     ballot + popc prefix, order preserving), so inactive rows are never addressed;
 //   * every thread owns four adjacent output columns; a warp streams its 512 contiguous bytes
-//     of every active row through a private cp.async ring in shared memory, kAspStages rows in
-//     flight per warp (commit/wait groups: a true FIFO, no register or scoreboard limits), and
-//     each lane reads back only the 16 bytes it copied itself, so no barrier is needed;
+//     of every active row — long lists with kAspRegs rows in flight in registers (plain 128-bit
+//     loads), short lists through a private cp.async ring in shared memory, kAspStages rows in
+//     flight per warp (commit/wait groups: a true FIFO, no register or scoreboard limits; each
+//     lane reads back only the 16 bytes it copied itself, so no barrier is needed);
 //   * row splits are summed in split order by the last CTA to arrive (integer ticket).
 // Deterministic, no floating-point atomics.
 #include <algorithm>
@@ -33,6 +34,30 @@ constexpr int kAspChunk = 1024;               // rows compacted per pass
 #define SPMV_ASP_STAGES 16
 #endif
 constexpr int kAspStages = SPMV_ASP_STAGES; // rows in flight per warp
+// > 0: the single-vector kernel keeps that many rows in flight per warp in REGISTERS (one 128-bit load per lane and
+// row, issued where it is written) instead of the cp.async ring: a ring costs LSU wavefronts twice (copy-in and
+// read-back, profiles/r02_notes.md), and 16 rows x 512 B x ~6 warps per SM is only ~50 KB in flight.
+// Same-box A/B, us per call on config 2 / 0 / 3 (ring = 16-deep cp.async ring for every chunk): ring 23.69 / 11.56 /
+// 9.31; registers for chunks with >= 96 active rows: 32 rows in flight 22.41 / 11.53 / 9.35, 40: 22.00 / 11.59 / 9.43,
+// 48: 21.76 / 11.55 / 9.46.  With 16 rows in flight registers LOSE to the ring (28.8 us): a warp has six scoreboards,
+// so waiting for the oldest of 16 loads also waits for younger ones that share its scoreboard, while cp.async groups
+// are an exact FIFO; the register path wins by depth (48 x 512 B per warp).  Short lists (config 3: ~45 active rows
+// per CTA) stay on the ring, whose ramp is cheaper.
+#ifndef SPMV_ASP_REGS
+#define SPMV_ASP_REGS 48
+#endif
+constexpr int kAspRegs = SPMV_ASP_REGS;
+#ifndef SPMV_ASP_REGS_MIN
+#define SPMV_ASP_REGS_MIN 96
+#endif
+constexpr int kAspRegsMin = SPMV_ASP_REGS_MIN;   // active rows in a CTA's chunk from which the register path is taken (below: the ring)
+
+__device__ __forceinline__ float4 asp_row_load(const float *p, bool ok)
+{
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
 
 // B > 1: batched form — B activation vectors x[b] (row stride ldx) against the
 // same A: a row is streamed once if ANY vector is active there and used for all of them (a vector
@@ -44,7 +69,7 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
            int splits, long long ldx, long long ldy)
 {
     __shared__ __align__(16) int rows_s[kAspChunk];
-    __shared__ float xs_s[B * kAspChunk];
+    __shared__ __align__(16) float xs_s[B * kAspChunk];
     __shared__ int wcnt[kAspThreads / 32];
     __shared__ int last_flag;
     extern __shared__ __align__(16) float4 ring_all[];    // (kAspThreads / 32) * kAspStages * 32
@@ -104,7 +129,41 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
         __syncthreads();
 
         // ---- stream the active rows ------------------------------------------------------------
-        if (col_ok) {
+        if (B == 1 && kAspRegs > 0 && total >= kAspRegsMin) {   // (block-uniform choice: depends on x only through `total`)
+            if (col_ok) {
+                constexpr int D = kAspRegs > 0 ? kAspRegs : 4;
+                float4 a[D];
+#pragma unroll
+                for (int k = 0; k < D; k += 4) {
+                    const int4 rw = *reinterpret_cast<const int4 *>(rows_s + k);   // (entries past `total` are stale: not used)
+                    a[k + 0] = asp_row_load(Ac + (long long)rw.x * ld, k + 0 < total);
+                    a[k + 1] = asp_row_load(Ac + (long long)rw.y * ld, k + 1 < total);
+                    a[k + 2] = asp_row_load(Ac + (long long)rw.z * ld, k + 2 < total);
+                    a[k + 3] = asp_row_load(Ac + (long long)rw.w * ld, k + 3 < total);
+                }
+                for (int i0 = 0; i0 < total; i0 += D) {
+#pragma unroll
+                    for (int k = 0; k < D; k += 4) {
+                        const int i = i0 + k;
+                        if (i >= total) break;                              // (block-uniform)
+                        const float4 xv = *reinterpret_cast<const float4 *>(xs_s + i);   // slots past `total`: their rows are zeros
+                        const int j = i + D;
+                        int4 rw = make_int4(0, 0, 0, 0);
+                        if (j < total) rw = *reinterpret_cast<const int4 *>(rows_s + (j & (kAspChunk - 1)));
+                        const float xk[4] = {xv.x, xv.y, xv.z, xv.w};
+                        const int rk[4] = {rw.x, rw.y, rw.z, rw.w};
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            if (i + q < total) {
+                                acc[0].x = fmaf(a[k + q].x, xk[q], acc[0].x); acc[0].y = fmaf(a[k + q].y, xk[q], acc[0].y);
+                                acc[0].z = fmaf(a[k + q].z, xk[q], acc[0].z); acc[0].w = fmaf(a[k + q].w, xk[q], acc[0].w);
+                            }
+                            a[k + q] = asp_row_load(Ac + (long long)rk[q] * ld, j + q < total);
+                        }
+                    }
+                }
+            }
+        } else if (col_ok) {
             auto issue = [&](int i) {
                 if (i < total)
                     cp_async16(ring + (i & (kAspStages - 1)) * 32 + lane,
