@@ -119,6 +119,11 @@ def test_group_several_slabs_on_one_gpu():
             off += w
         part = g.run_host(x, y_begin=512, y_count=1024)
         assert part.tobytes() == ys[0][512:1536].tobytes()
+        # the copy-back pipeline (one event per slab, second stream): ranges that cross slab boundaries, the full range,
+        # a single column, repeated calls (both y buffers)
+        for b, c in ((0, N), (100, 1000), (508, 8), (1536 - 4, 2048), (N - 1, 1), (0, 1)):
+            for _ in range(2):
+                assert g.run_host(x, y_begin=b, y_count=c).tobytes() == ys[0][b:b + c].tobytes(), (b, c)
         g.status()
         with pytest.raises(S.SpmvError):
             g.add(plans[0], N - 4)                        # does not fit
