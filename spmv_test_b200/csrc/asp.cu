@@ -62,7 +62,9 @@ __device__ __forceinline__ float4 asp_row_load(const float *p, bool ok)
 // B > 1: batched form — B activation vectors x[b] (row stride ldx) against the
 // same A: a row is streamed once if ANY vector is active there and used for all of them (a vector
 // with x[b][row] == 0 adds an exact zero), so every y[b] is bit-identical to a single-vector call.
-template <int B>
+// R: rows in flight in registers for long lists (0: the ring only — the instance plans with short row ranges get,
+// whose register count then stays small).
+template <int B, int R>
 __global__ void __launch_bounds__(kAspThreads)
 asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ x, const YDst yd,
            float *__restrict__ partial, unsigned *__restrict__ tickets, int M, int N, int rows_per_split,
@@ -129,9 +131,9 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
         __syncthreads();
 
         // ---- stream the active rows ------------------------------------------------------------
-        if (B == 1 && kAspRegs > 0 && total >= kAspRegsMin) {   // (block-uniform choice: depends on x only through `total`)
+        if (B == 1 && R > 0 && total >= kAspRegsMin) {   // (block-uniform choice: depends on x only through `total`)
             if (col_ok) {
-                constexpr int D = kAspRegs > 0 ? kAspRegs : 4;
+                constexpr int D = R > 0 ? R : 4;
                 float4 a[D];
 #pragma unroll
                 for (int k = 0; k < D; k += 4) {
@@ -211,16 +213,16 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
 
 } // namespace
 
-template <int B>
+template <int B, int R = 0>
 static int launch_asp_b(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st, long long ldx, long long ldy)
 {
     const int smem = (kAspThreads / 32) * kAspStages * 32 * (int)sizeof(float4);
     static int smem_set[16] = {0};   // static + dynamic shared memory exceeds 48 KB for B = 4: always opt in
     if (p->device >= 0 && p->device < 16 && smem_set[p->device] < smem) {
-        SPMV_CUDA(cudaFuncSetAttribute(asp_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SPMV_CUDA(cudaFuncSetAttribute(asp_kernel<B, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         smem_set[p->device] = smem;
     }
-    SPMV_CUDA(launch_k(asp_kernel<B>, p->grid, dim3(kAspThreads), smem, st, p->asp.A, (long long)p->asp.ld, d_x, yd, p->partial,
+    SPMV_CUDA(launch_k(asp_kernel<B, R>, p->grid, dim3(kAspThreads), smem, st, p->asp.A, (long long)p->asp.ld, d_x, yd, p->partial,
                        p->tickets, (int)p->M, (int)p->N, p->asp.rows_per_split, p->row_splits, ldx, ldy));
     return SPMV_OK;
 }
@@ -228,6 +230,8 @@ static int launch_asp_b(spmv_plan *p, const float *d_x, const YDst &yd, cudaStre
 int launch_asp(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st)
 {
     if (p->N == 0) return SPMV_OK;
+    // a CTA's row range must be able to hold a long list at all (x decides at run time, chunk by chunk)
+    if (kAspRegs > 0 && p->asp.rows_per_split >= 2 * kAspRegsMin) return launch_asp_b<1, kAspRegs>(p, d_x, yd, st, 0, 0);
     return launch_asp_b<1>(p, d_x, yd, st, 0, 0);
 }
 
