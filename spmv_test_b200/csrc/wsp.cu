@@ -14,6 +14,7 @@
 // cross-warp sum.  No atomics.
 #include <algorithm>
 #include <climits>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -318,7 +319,8 @@ wsp_ring_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
     x += (size_t)panel * panel_rows;
     colptr += (size_t)panel * n_total;
     float4 *ring_v = reinterpret_cast<float4 *>(wsm + xs_bytes) + warp * kRingStages * 32;
-    IdxVec *ring_i = reinterpret_cast<IdxVec *>(wsm + xs_bytes + kRingWarps * kRingStages * 32 * 16) + warp * kRingStages * 32;
+    const int wpc = blockDim.x >> 5;                      // warps per CTA: 4 .. kRingWarps, chosen per plan (configure_wsp)
+    IdxVec *ring_i = reinterpret_cast<IdxVec *>(wsm + xs_bytes + wpc * kRingStages * 32 * 16) + warp * kRingStages * 32;
 
     pdl_wait();
     // x -> shared memory (1-D bulk async copies when aligned), overlapped with the first chunks
@@ -348,8 +350,8 @@ wsp_ring_kernel(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
     // This warp's columns are positions kbase, kbase + nwarps, ... of the column list.  Their
     // (column id, first group, end group) are fetched 32 at a time — lane l holds the l-th
     // upcoming column — one batch ahead of use, so even one-chunk columns keep the ring full.
-    const int nwarps = gridDim.x * kRingWarps;
-    const int kbase = blockIdx.x * kRingWarps + warp;
+    const int nwarps = gridDim.x * wpc;
+    const int kbase = blockIdx.x * wpc + warp;
     int bc = -1, nc = -1; uint32_t b0 = 0, b1 = 0, n0 = 0, n1 = 0;   // current / next batch (per lane)
     int jb = 0;                                            // index of the next column inside the current batch
     int batch0 = 0;                                        // list position (in this warp's sequence) of the next batch
@@ -454,7 +456,7 @@ struct Bin { int T; std::vector<int32_t> cols; };
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-struct WspBinDev { int T; int32_t *cols; int ncols; int grid; bool ring; int smem; };
+struct WspBinDev { int T; int32_t *cols; int ncols; int grid; bool ring; int smem; int warps; };   // warps: per CTA of the ring kernel
 
 struct WspState {            // hangs off the plan through plan->wsp_state
     std::vector<WspBinDev> bins;
@@ -508,7 +510,7 @@ static int launch_ring(const spmv_plan *p, const WspBinDev &b, const float *x, c
         smem_set[p->device] = smem;
     }
     const WspState *ws = reinterpret_cast<const WspState *>(p->wsp_state);
-    SPMV_CUDA(launch_k(k, dim3(b.grid, ws->panels), dim3(kRingWarps * 32), smem, st, reinterpret_cast<const float4 *>(p->wsp.vals),
+    SPMV_CUDA(launch_k(k, dim3(b.grid, ws->panels), dim3((b.warps > 0 ? b.warps : kRingWarps) * 32), smem, st, reinterpret_cast<const float4 *>(p->wsp.vals),
                        reinterpret_cast<const IdxVec *>(p->wsp.idx), p->wsp.colptr, b.cols, b.ncols, x, y, (uint32_t)p->M, ok,
                        xs_bytes, (uint32_t)ws->panel_rows, (int)p->N, ws->partial, ldx, ldy));
     if (ws->panels > 1)
@@ -602,8 +604,10 @@ int configure_wsp(spmv_plan *p, const HostWsp &w, const spmv_options_t *o)
     // ---- row-length binning --------------------------------------------------------------
     // target ~8 groups (32 non-zeros) per thread; bins are powers of two in [4, 256].
     const int64_t N = w.N;
+    int gpt = 8;
+    if (const char *e = std::getenv("SPMV_WSP_GROUPS_PER_THREAD")) gpt = std::max(1, std::atoi(e));   // development knob
     auto team_for = [&](int64_t groups) {
-        int t = pow2_ceil((groups + 7) / 8);
+        int t = pow2_ceil((groups + gpt - 1) / gpt);
         return std::min(256, std::max(4, t));
     };
     int64_t gmin = INT64_MAX, gmax = 0;
@@ -649,10 +653,41 @@ int configure_wsp(spmv_plan *p, const HostWsp &w, const spmv_options_t *o)
         if (p->wsp.x_in_smem && (b.T >= 32 || w.panels > 1) && !(o && o->warps_per_col > 0 && w.panels == 1)) {
             // long columns: warp per column through the cp.async ring
             d.ring = true;
-            d.smem = p->smem + kRingWarps * kRingStages * 32 * (16 + (w.index_bits == 16 ? 8 : 16));
-            const int resident = std::max(1, std::min(8, (220 * 1024) / (d.smem + 1024)));
+            const int chunk_bytes = 32 * (16 + (w.index_bits == 16 ? 8 : 16));
+            auto ring_smem = [&](int warps) { return p->smem + warps * kRingStages * chunk_bytes; };
+            auto resident_of = [&](int warps) { return std::max(1, std::min(8, (220 * 1024) / (ring_smem(warps) + 1024))); };
+            d.warps = kRingWarps;
+            d.smem = ring_smem(kRingWarps);
+            const int resident = resident_of(kRingWarps);
             const int64_t want = ((int64_t)d.ncols + kRingWarps - 1) / kRingWarps;
             d.grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, ((int64_t)p->sm_count * resident + w.panels - 1) / w.panels));
+            // Whole columns are dealt to the warps, so with more columns than resident warps the kernel lasts
+            // ceil(columns / warps) columns while the average warp has columns / warps of them: config 2's 14336
+            // columns on 3552 warps (three 8-warp CTAs per SM) are 4.04 per warp — 128 warps stream a fifth column
+            // alone at the end (0.81 of the rate); config 0's 4096 on 3552 are 1.15 -> 2 (0.58).  Choose the
+            // geometry (CTAs per SM, 4..8 warps per CTA; one resident wave) that wastes least, preferring more warps.
+            // Same-box A/B, us per call, config 2 / 0 / 3: three 8-warp CTAs per SM (round 1) 22.36 / 13.02 / 22.69;
+            // 3 x 7 22.18 / 12.96 / 22.17; 3 x 6 21.41 / 12.64 / 24.05; 2 x 8 21.35 / 12.07 / 21.49; 2 x 7 (what this
+            // rule picks for all three) 21.15 / 11.65 / 21.18.  A 12-deep ring instead of 8 is slower everywhere.
+            if (w.panels == 1 && d.ncols > p->sm_count * resident * kRingWarps) {
+                double best = 0.0;
+                for (int wp = kRingWarps; wp >= 4; wp--) {
+                    for (int c = resident_of(wp); c >= 1; c--) {
+                        const int64_t wt = (int64_t)p->sm_count * c * wp;
+                        if (wt < (int64_t)p->sm_count * 12) continue;         // keep at least 12 warps per SM streaming
+                        const int64_t cpw = (d.ncols + wt - 1) / wt;
+                        const double eff = (double)d.ncols / ((double)wt * (double)cpw);
+                        if (eff > best + 0.02) { best = eff; d.warps = wp; d.grid = p->sm_count * c; d.smem = ring_smem(wp); }
+                    }
+                }
+            }
+            if (const char *e = std::getenv("SPMV_WSP_RING_GEOM")) {      // development knob: "ctas_per_sm,warps_per_cta"
+                int c = 0, wp = 0;
+                if (std::sscanf(e, "%d,%d", &c, &wp) == 2 && c >= 1 && wp >= 1 && wp <= kRingWarps) {
+                    d.warps = wp; d.smem = ring_smem(wp);
+                    d.grid = (int)std::min<int64_t>(((int64_t)d.ncols + wp - 1) / wp, (int64_t)p->sm_count * c);
+                }
+            }
         }
         s->bins.push_back(d);
     }

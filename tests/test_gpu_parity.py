@@ -144,6 +144,27 @@ def test_column_slab_view_with_lda(S):
                 check_y(p.run_host(x), y32[a:b], y64[a:b], s[a:b], f"{v} slab {a}:{b}")
 
 
+def test_asp_register_path_long_and_short_lists(S):
+    """asp streams chunks with >= 96 active rows with the rows in flight in registers and shorter lists through the
+    cp.async ring (asp.cu, kAspRegsMin), in ONE kernel: a CTA whose first 1024-row chunk is long and whose second is
+    short, a column tile that ends inside a 512-column tile, a slab view (lda > N), exactly 96 / 95 active rows,
+    and a list length that is not a multiple of the four-row groups."""
+    M, N = 2048, 992                                         # (N must be a multiple of 32: tester.cpp:9-10)
+    wide = ob.gen_matrix(M, N + 32, 0.3, 77)
+    A = wide[:, 16:16 + N]                                   # lda = N + 32
+    for active_lo, active_hi in ((1024, 3), (96, 0), (95, 95), (513, 97), (0, 1024)):
+        x = np.zeros(M, np.float32)
+        rng = np.random.default_rng(active_lo * 7 + active_hi)
+        x[rng.choice(1024, active_lo, replace=False)] = rng.uniform(-1, 1, active_lo).astype(np.float32)
+        x[1024 + rng.choice(1024, active_hi, replace=False)] = rng.uniform(-1, 1, active_hi).astype(np.float32)
+        y32, y64, s = refs(np.ascontiguousarray(A), x)
+        for splits in (1, 2, 5):
+            with S.Plan.from_dense("asp", A, row_splits=splits) as p:
+                y = p.run_host(x)
+                check_y(y, y32, y64, s, f"asp registers/ring {active_lo}+{active_hi} splits {splits}")
+                assert p.run_host(x).tobytes() == y.tobytes()
+
+
 @pytest.mark.parametrize("opts", [dict(row_splits=1), dict(row_splits=3), dict(row_splits=64),
                                   dict(slab_cols=512), dict(slab_cols=4096), dict(index_bits=32),
                                   dict(warps_per_col=1), dict(warps_per_col=8), dict(chunk_mode=1), dict(chunk_mode=2),
