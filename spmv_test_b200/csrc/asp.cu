@@ -34,12 +34,14 @@ constexpr int kAspChunk = 1024;               // rows compacted per pass
 #define SPMV_ASP_STAGES 16
 #endif
 constexpr int kAspStages = SPMV_ASP_STAGES; // rows in flight per warp
+static_assert((kAspStages & (kAspStages - 1)) == 0, "the ring is indexed with a mask");
 // > 0: the single-vector kernel keeps that many rows in flight per warp in REGISTERS (one 128-bit load per lane and
 // row, issued where it is written) instead of the cp.async ring: a ring costs LSU wavefronts twice (copy-in and
 // read-back, profiles/r02_notes.md), and 16 rows x 512 B x ~6 warps per SM is only ~50 KB in flight.
 // Same-box A/B, us per call on config 2 / 0 / 3 (ring = 16-deep cp.async ring for every chunk): ring 23.69 / 11.56 /
-// 9.31; registers for chunks with >= 96 active rows: 32 rows in flight 22.41 / 11.53 / 9.35, 40: 22.00 / 11.59 / 9.43,
-// 48: 21.76 / 11.55 / 9.46.  With 16 rows in flight registers LOSE to the ring (28.8 us): a warp has six scoreboards,
+// 9.31; registers for chunks with >= 96 active rows (plans whose row ranges hold 192 rows): 32 rows in flight 22.41 / 11.53 / 9.35, 40: 22.00 / 11.59 / 9.43,
+// 48: 21.76 / 11.55 / 9.46; 48 rows for chunks with >= 48 active rows (kept): 21.74 / 11.54 / 9.22 against 21.73 /
+// 11.70 / 9.57 on that box; a 32-deep ring for the short lists: 21.79 / 12.03 / 10.00.  With 16 rows in flight registers LOSE to the ring (28.8 us): a warp has six scoreboards,
 // so waiting for the oldest of 16 loads also waits for younger ones that share its scoreboard, while cp.async groups
 // are an exact FIFO; the register path wins by depth (48 x 512 B per warp).  Short lists (config 3: ~45 active rows
 // per CTA) stay on the ring, whose ramp is cheaper.
@@ -48,7 +50,7 @@ constexpr int kAspStages = SPMV_ASP_STAGES; // rows in flight per warp
 #endif
 constexpr int kAspRegs = SPMV_ASP_REGS;
 #ifndef SPMV_ASP_REGS_MIN
-#define SPMV_ASP_REGS_MIN 96
+#define SPMV_ASP_REGS_MIN 48
 #endif
 constexpr int kAspRegsMin = SPMV_ASP_REGS_MIN;   // active rows in a CTA's chunk from which the register path is taken (below: the ring)
 

@@ -145,14 +145,14 @@ def test_column_slab_view_with_lda(S):
 
 
 def test_asp_register_path_long_and_short_lists(S):
-    """asp streams chunks with >= 96 active rows with the rows in flight in registers and shorter lists through the
+    """asp streams chunks with >= 48 active rows with the rows in flight in registers and shorter lists through the
     cp.async ring (asp.cu, kAspRegsMin), in ONE kernel: a CTA whose first 1024-row chunk is long and whose second is
-    short, a column tile that ends inside a 512-column tile, a slab view (lda > N), exactly 96 / 95 active rows,
-    and a list length that is not a multiple of the four-row groups."""
+    short, a column tile that ends inside a 512-column tile, a slab view (lda > N), list lengths on both sides of the
+    threshold and of the pipeline depth, and lengths that are not a multiple of the four-row groups."""
     M, N = 2048, 992                                         # (N must be a multiple of 32: tester.cpp:9-10)
     wide = ob.gen_matrix(M, N + 32, 0.3, 77)
     A = wide[:, 16:16 + N]                                   # lda = N + 32
-    for active_lo, active_hi in ((1024, 3), (96, 0), (95, 95), (513, 97), (0, 1024)):
+    for active_lo, active_hi in ((1024, 3), (96, 0), (95, 95), (513, 97), (0, 1024), (48, 47), (49, 0), (1, 50)):
         x = np.zeros(M, np.float32)
         rng = np.random.default_rng(active_lo * 7 + active_hi)
         x[rng.choice(1024, active_lo, replace=False)] = rng.uniform(-1, 1, active_lo).astype(np.float32)
