@@ -46,6 +46,15 @@ constexpr bool kStripRegs = SPMV_STRIP_REGS != 0;
 #define SPMV_STRIP_PREFETCH 0
 #endif
 constexpr bool kStripPrefetch = SPMV_STRIP_PREFETCH != 0;
+// batches of per-row scalars (segment offsets, x) in flight ahead of the one being parked: with one, the park at the
+// top of a batch was the kernel's largest single stall site (ncu: 1125 of ~5400 samples on the subtraction that first
+// uses the loaded offsets) — under a saturated LSU pipe a global load needs more than one batch time to return.
+// Two batches ahead removes that stall and changes the time by 0.1 % (93.87 against 93.97-94.07 us per slab, three
+// alternating runs on one box): the pipe's wavefronts, not the warps' stalls, set the time.
+#ifndef SPMV_STRIP_META_AHEAD
+#define SPMV_STRIP_META_AHEAD 2
+#endif
+constexpr int kStripMetaAhead = SPMV_STRIP_META_AHEAD;
 // (four rows share one cp.async commit group and one set of broadcast loads of their scalars)
 constexpr int kStripSub = 2048;                           // rows compacted per pass
 constexpr int kStripSpan = kStripSub / kStripWarps;       // rows a warp compacts: 128
@@ -230,6 +239,7 @@ strips_kernel(const uint2 *__restrict__ ent, const uint32_t *__restrict__ soff, 
         park(sl_of(0), xs_of(0), load_meta(0));
         park(sl_of(1), xs_of(1), load_meta(32));
         Meta ahead = load_meta(64);
+        Meta ahead2 = kStripMetaAhead > 1 ? load_meta(96) : Meta{0u, 0u, 0u};   // (a second batch of scalars in flight)
         __syncwarp();
         constexpr int kGroups = kStripStages / 4;         // groups of four rows in flight
         uint2 E[kGroups][4];
@@ -241,8 +251,9 @@ strips_kernel(const uint2 *__restrict__ ent, const uint32_t *__restrict__ soff, 
         }
 #pragma unroll 1
         for (int bi = 0; bi * 32 < total; bi++) {
-            park(sl_of(bi + 2), xs_of(bi + 2), ahead);    // (its loads had a whole batch to land)
-            ahead = load_meta((bi + 3) * 32);
+            park(sl_of(bi + 2), xs_of(bi + 2), ahead);    // (its loads had one or two whole batches to land)
+            if (kStripMetaAhead > 1) { ahead = ahead2; ahead2 = load_meta((bi + 4) * 32); }
+            else ahead = load_meta((bi + 3) * 32);
             __syncwarp();
             const uint2 *sl0 = sl_of(bi), *sl1 = sl_of(bi + 1), *sl2 = sl_of(bi + 2);
             const float *xs0 = xs_of(bi);
