@@ -97,9 +97,14 @@ wsp_body(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
         __syncthreads();
     }
 
-    for (int k = team; k < ncols; k += nteams) {
-        const int c = cols ? cols[k] : k;
-        const uint32_t g0 = colptr[c], g1 = colptr[c + 1];
+    // Sub-warp teams share a warp and the shuffles below name all 32 lanes, so every team of a warp makes the same
+    // number of trips: a team past the end of the list walks an empty column and stores nothing.
+    for (int k = team;; k += nteams) {
+        const bool act = k < ncols;
+        if (T < 32 ? !__any_sync(kFull, act) : !act) break;
+        const int c = act ? (cols ? cols[k] : k) : 0;
+        uint32_t g0 = 0u, g1 = 0u;
+        if (act) { g0 = colptr[c]; g1 = colptr[c + 1]; }
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         for (uint32_t g = g0 + tl; g < g1; g += T * kWspUnroll) {
             float4 v[kWspUnroll];
@@ -145,7 +150,7 @@ wsp_body(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx,
         } else {
 #pragma unroll
             for (int s = T / 2; s >= 1; s >>= 1) acc += __shfl_xor_sync(kFull, acc, s);
-            if (tl == 0) y_store(yd, c, acc);
+            if (tl == 0 && act) y_store(yd, c, acc);
         }
     }
 }
@@ -174,7 +179,8 @@ wsp_body_short(const float4 *__restrict__ vals, const IdxVec *__restrict__ idx, 
     constexpr int kTeams = kWspBlock / T;
     const int tid = threadIdx.x, tl = tid % T;
     const int team = bid * kTeams + tid / T, nteams = nblocks * kTeams;
-    for (int k0 = team * C; k0 < ncols; k0 += nteams * C) {
+    for (int k0 = team * C;; k0 += nteams * C) {            // (same trip count for every team of a warp: see wsp_body)
+        if (T < 32 ? !__any_sync(kFull, k0 < ncols) : !(k0 < ncols)) break;
         int c[C];
         uint32_t g0[C], g1[C];
 #pragma unroll
