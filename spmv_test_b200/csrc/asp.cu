@@ -15,6 +15,10 @@
 //   * row splits are summed in split order by the last CTA to arrive (integer ticket).
 // Deterministic, no floating-point atomics.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include <cuda.h>      // CUtensorMap and its enums only: the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link)
 
 #include "common.cuh"
 #include "plan.hpp"
@@ -213,6 +217,152 @@ asp_kernel(const float *__restrict__ A, long long ld, const float *__restrict__ 
     }
 }
 
+// ---- TMA row gather (cp.async.bulk.tensor.2d ... tile::gather4) ---------------------------------------------
+// The single-vector kernel with the rows moved by the TMA engine instead of the SM's load/store units: a fifth warp's
+// lane 0 walks the compacted row list four rows at a time and issues, per group, two gather4 copies (4 arbitrary rows
+// x 256 columns = 4 KB each; the tensor map's box is 256 x 1) into a ring of kAspTmaStages 8 KB stages guarded by
+// full (transaction bytes) / empty (128 arrivals) mbarriers; the four consumer warps read their 16 bytes of each row
+// back and do the same FMAs in the same order as asp_kernel, so y is bit-identical to it.  Micro-benchmark of the bare
+// access pattern on config 2 (tools/ubench/gather4.cu, same box): 18.75 us against 20.77 us for 32 rows in flight in
+// registers (4 stages 20.3, 12 stages 19.3).  In the real kernel — compaction in front, FMAs, split reduction behind
+// — it LOSES to the register / ring kernel: config 2 / 0 / 3 24.22 / 12.14 / 9.26 us against 21.91 / 11.55 / 9.21
+// (same box, parity tests green on both), so it is not the default: SPMV_ASP_TMA=1 selects it.
+#ifndef SPMV_ASP_TMA_DEFAULT
+#define SPMV_ASP_TMA_DEFAULT 0
+#endif
+#ifndef SPMV_ASP_TMA_STAGES
+#define SPMV_ASP_TMA_STAGES 8
+#endif
+constexpr int kAspTmaStages = SPMV_ASP_TMA_STAGES;
+constexpr int kAspTmaThreads = kAspThreads + 32;
+struct alignas(64) AspTmap { unsigned char b[128]; };
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kAspTmaThreads)
+asp_tma_kernel(const __grid_constant__ AspTmap tm, const float *__restrict__ x, const YDst yd, float *__restrict__ partial,
+               unsigned *__restrict__ tickets, int M, int N, int rows_per_split, int splits)
+{
+    static_assert(kAspThreads == 128 && kAspTile == 512, "two 256-column boxes per tile, four consumer warps");
+    __shared__ __align__(16) int rows_s[kAspChunk];
+    __shared__ __align__(16) float xs_s[kAspChunk];
+    __shared__ int wcnt[kAspThreads / 32];
+    __shared__ int last_flag;
+    __shared__ __align__(8) uint64_t full[kAspTmaStages], empty[kAspTmaStages];
+    extern __shared__ unsigned char tma_raw[];
+    unsigned char *stage = tma_raw + ((1024u - (smem_u32(tma_raw) & 1023u)) & 1023u);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x, split = blockIdx.y;
+    const int c0 = tile * kAspTile + tid * 4;
+    const bool consumer = warp < kAspThreads / 32;
+    const bool col_ok = consumer && c0 < N;
+    const int halves = tile * kAspTile + 256 < N ? 2 : 1;  // a tile's second box may lie past N: not requested
+    const int r_begin = split * rows_per_split;
+    const int r_end = min(M, r_begin + rows_per_split);
+    if (tid == 0) {
+        for (int s = 0; s < kAspTmaStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kAspThreads); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    pdl_wait();
+    unsigned gdone = 0;                                   // four-row groups through the ring so far (same in every thread)
+    for (int r0 = r_begin; r0 < r_end; r0 += kAspChunk) {
+        constexpr int kSpan = kAspChunk / (kAspThreads / 32);
+        constexpr int kSteps = kSpan / 32;
+        float xr[kSteps]; unsigned bal[kSteps];
+        int cnt = 0;
+        if (consumer) {
+#pragma unroll
+            for (int k = 0; k < kSteps; k++) {
+                const int row = r0 + warp * kSpan + k * 32 + lane;
+                xr[k] = row < r_end ? __ldg(x + row) : 0.0f;
+                bal[k] = __ballot_sync(kFull, xr[k] != 0.0f);
+                cnt += __popc(bal[k]);
+            }
+        }
+        __syncthreads();                                  // previous chunk's list fully consumed (by the producer too)
+        if (consumer && lane == 0) wcnt[warp] = cnt;
+        __syncthreads();
+        int base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kAspThreads / 32; w++) {
+            const int cw = wcnt[w];
+            if (w < warp) base += cw;
+            total += cw;
+        }
+        if (consumer) {
+            const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int k = 0; k < kSteps; k++) {
+                if (bal[k] & (1u << lane)) {
+                    const int pos = base + __popc(bal[k] & lt);
+                    rows_s[pos] = r0 + warp * kSpan + k * 32 + lane;
+                    xs_s[pos] = xr[k];
+                }
+                base += __popc(bal[k]);
+            }
+        }
+        __syncthreads();
+
+        const int ngroups = (total + 3) >> 2;
+        if (!consumer) {
+            if (lane == 0) {
+                for (int g = 0; g < ngroups; g++) {
+                    const unsigned gg = gdone + (unsigned)g;
+                    const int s = (int)(gg % kAspTmaStages);
+                    if (gg >= (unsigned)kAspTmaStages) mbar_wait(&empty[s], ((gg / kAspTmaStages) - 1u) & 1u);
+                    mbar_expect_tx(&full[s], (uint32_t)halves * 4096u);
+                    int rr[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) rr[q] = rows_s[min(4 * g + q, total - 1)];   // a short last group repeats its last row
+                    for (int h = 0; h < halves; h++)
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes "
+                                     "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                                     ::"r"(smem_u32(stage + s * 8192 + h * 4096)), "l"(&tm), "r"(tile * kAspTile + h * 256), "r"(rr[0]),
+                                     "r"(rr[1]), "r"(rr[2]), "r"(rr[3]), "r"(smem_u32(&full[s])) : "memory");
+                }
+            }
+        } else {
+            for (int g = 0; g < ngroups; g++) {
+                const unsigned gg = gdone + (unsigned)g;
+                const int s = (int)(gg % kAspTmaStages);
+                mbar_wait(&full[s], (gg / kAspTmaStages) & 1u);
+                if (col_ok) {
+                    const float4 *rowp = reinterpret_cast<const float4 *>(stage + s * 8192 + (tid >> 6) * 4096) + (tid & 63);
+                    const float4 xv = *reinterpret_cast<const float4 *>(xs_s + 4 * g);     // (slots past `total` are stale: not used)
+                    const float xk[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (4 * g + q < total) {
+                            const float4 a = rowp[q * 64];
+                            acc.x = fmaf(a.x, xk[q], acc.x); acc.y = fmaf(a.y, xk[q], acc.y);
+                            acc.z = fmaf(a.z, xk[q], acc.z); acc.w = fmaf(a.w, xk[q], acc.w);
+                        }
+                    }
+                }
+                mbar_arrive(&empty[s]);
+            }
+        }
+        gdone += (unsigned)ngroups;
+    }
+
+    if (splits == 1) {
+        if (col_ok) y_store4(yd, (size_t)c0 >> 2, acc);
+        return;
+    }
+    const size_t npad = (size_t)gridDim.x * kAspTile;
+    const int n_valid = min(kAspTile, N - tile * kAspTile);
+    if (consumer) *reinterpret_cast<float4 *>(partial + (size_t)split * npad + (size_t)tile * kAspTile + tid * 4) = acc;
+    __syncthreads();                                      // the row list is dead: reuse it as scratch
+    split_reduce_finish(yd, partial, tickets, tile, splits, kAspTile, n_valid, npad, &last_flag, reinterpret_cast<float4 *>(rows_s));
+}
+
 } // namespace
 
 template <int B, int R = 0>
@@ -229,9 +379,65 @@ static int launch_asp_b(spmv_plan *p, const float *d_x, const YDst &yd, cudaStre
     return SPMV_OK;
 }
 
+// The tensor map of this plan's A for asp_tma_kernel: box = 256 columns x 1 row (what tile::gather4 requires: a box of
+// four rows is an illegal instruction), no swizzle, 128-byte L2 promotion.  Encoded once per (plan, buffer).
+static bool asp_tma_ready(spmv_plan *p)
+{
+    DevAsp &a = p->asp;
+    if (a.tma_state == 1 && a.tmap_for == a.A) return true;
+    if (a.tma_state < 0 && a.tmap_for == a.A) return false;
+    a.tmap_for = a.A;
+    a.tma_state = -1;
+    static_assert(sizeof(CUtensorMap) == sizeof(a.tmap), "tensor maps are 128 bytes");
+    typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+        cudaGetLastError();
+        return reinterpret_cast<EncodeTiled>(fn);
+    }();
+    if (!encode || p->N < 256 || p->M < 1 || (a.ld & 3) || (reinterpret_cast<uintptr_t>(a.A) & 15)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)p->N, (cuuint64_t)p->M};
+    const cuuint64_t strides[1] = {(cuuint64_t)a.ld * 4};
+    const cuuint32_t box[2] = {256u, 1u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    if (encode(reinterpret_cast<CUtensorMap *>(a.tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.A, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    a.tma_state = 1;
+    return true;
+}
+
+// 1: single-vector asp calls go through asp_tma_kernel when the plan's matrix can be described by a tensor map
+static bool asp_tma_wanted()
+{
+    static const int on = [] { const char *e = std::getenv("SPMV_ASP_TMA"); return e ? std::atoi(e) : SPMV_ASP_TMA_DEFAULT; }();
+    return on != 0;
+}
+
+static int launch_asp_tma(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st)
+{
+    const int smem = kAspTmaStages * 8192 + 1024;
+    static int smem_set[16] = {0};
+    if (p->device >= 0 && p->device < 16 && !smem_set[p->device]) {
+        SPMV_CUDA(cudaFuncSetAttribute(asp_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set[p->device] = 1;
+    }
+    AspTmap tm;
+    std::memcpy(tm.b, p->asp.tmap, sizeof tm.b);
+    SPMV_CUDA(launch_k(asp_tma_kernel, p->grid, dim3(kAspTmaThreads), (size_t)smem, st, tm, d_x, yd, p->partial, p->tickets, (int)p->M,
+                       (int)p->N, p->asp.rows_per_split, p->row_splits));
+    return SPMV_OK;
+}
+
 int launch_asp(spmv_plan *p, const float *d_x, const YDst &yd, cudaStream_t st)
 {
     if (p->N == 0) return SPMV_OK;
+    if (asp_tma_wanted() && asp_tma_ready(p)) return launch_asp_tma(p, d_x, yd, st);
     // a CTA's row range must be able to hold a long list at all (x decides at run time, chunk by chunk)
     if (kAspRegs > 0 && p->asp.rows_per_split >= 2 * kAspRegsMin) return launch_asp_b<1, kAspRegs>(p, d_x, yd, st, 0, 0);
     return launch_asp_b<1>(p, d_x, yd, st, 0, 0);

@@ -81,6 +81,11 @@ struct DevAsp {
     int64_t ld = 0;
     int tile_cols = 0;      // columns per CTA
     int rows_per_split = 0;
+    // TMA row-gather path (asp.cu: asp_tma_kernel): a 2-D tensor map of A with a (256 columns x 1 row) box, encoded at
+    // the first launch for the buffer it describes (a clone has its own A, so it encodes its own)
+    alignas(64) unsigned char tmap[128] = {};
+    const float *tmap_for = nullptr;
+    int tma_state = 0;      // 0: not tried yet, 1: usable, -1: not available (driver entry point, alignment)
 };
 
 struct DevPanel {
