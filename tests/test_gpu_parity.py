@@ -165,6 +165,51 @@ def test_asp_register_path_long_and_short_lists(S):
                 assert p.run_host(x).tobytes() == y.tobytes()
 
 
+_TMA_CHILD = r"""
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, {here!r}); sys.path.insert(0, {root!r})
+import oracle_bindings as ob
+from parity import check_y
+import spmv_test_b200 as S
+M, N = 2048, 992
+wide = ob.gen_matrix(M, N + 32, 0.3, 77)
+A = wide[:, 16:16 + N]
+for seed, sx in ((1, 0.5), (2, 0.97), (3, 0.0)):
+    x = ob.gen_vector(M, sx, 900 + seed)
+    y32 = ob.sgemv_dense(np.ascontiguousarray(A), x)
+    y64, s = ob.sgemv_dense_f64(np.ascontiguousarray(A), x)
+    for splits in (1, 3, 0):
+        with S.Plan.from_dense("asp", A, row_splits=splits) as p:
+            y = p.run_host(x)
+            check_y(y, y32, y64, s, "asp tma")
+            print(seed, splits, hashlib.sha256(y.tobytes()).hexdigest())
+"""
+
+
+def test_asp_tma_row_gather_path(S):
+    """asp_tma_kernel (cp.async.bulk.tensor ... tile::gather4, selected with SPMV_ASP_TMA=1 — read once per process, hence
+    the child process): inside the parity gate against the oracle and BIT-IDENTICAL to the default kernel (same FMAs in
+    the same order) on a slab view (lda > N), a last tile that ends inside its second 256-column box, dense / half /
+    3 % active x, one, three and the default number of row splits."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    code = _TMA_CHILD.format(here=here, root=root)
+
+    def run(env_val):
+        env = dict(os.environ, SPMV_ASP_TMA=env_val)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return r.stdout.strip().splitlines()
+
+    with_tma, without = run("1"), run("0")
+    assert len(with_tma) == 9 and with_tma == without
+
+
 @pytest.mark.parametrize("opts", [dict(row_splits=1), dict(row_splits=3), dict(row_splits=64),
                                   dict(slab_cols=512), dict(slab_cols=4096), dict(index_bits=32),
                                   dict(warps_per_col=1), dict(warps_per_col=8), dict(chunk_mode=1), dict(chunk_mode=2),
