@@ -423,9 +423,10 @@ static int launch_asp_tma(spmv_plan *p, const float *d_x, const YDst &yd, cudaSt
 {
     const int smem = kAspTmaStages * 8192 + 1024;
     static int smem_set[16] = {0};
-    if (p->device >= 0 && p->device < 16 && !smem_set[p->device]) {
+    const bool cached = p->device >= 0 && p->device < 16;
+    if (!cached || !smem_set[p->device]) {                // (beyond 16 devices: set on every call, the opt-in is mandatory)
         SPMV_CUDA(cudaFuncSetAttribute(asp_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        smem_set[p->device] = 1;
+        if (cached) smem_set[p->device] = 1;
     }
     AspTmap tm;
     std::memcpy(tm.b, p->asp.tmap, sizeof tm.b);
