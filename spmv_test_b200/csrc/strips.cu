@@ -11,12 +11,14 @@
 //     pieces) while each warp only ever touches its private strip accumulators in shared memory;
 //   * the CTA compacts its x slice once (ballot + popc, order preserving: the x != 0.0f test of
 //     awsp.cu:98,127) into a shared list of active rows; rows with x == 0 are never addressed;
-//   * per active row a warp copies its strip segment — one 8-byte entry per lane, idle lanes
-//     zero-filled — through a 16-deep cp.async ring and retires it in ONE pass: the entries of
-//     one row are distinct columns, so no two lanes meet in an accumulator (no passes, no votes,
-//     no predicates: a zero-filled lane adds 0 to accumulator 0, columns are stored + 1);
-//   * per-row scalars (segment start, length, x) are fetched lane = row, two 32-row batches ahead,
-//     into a small per-warp table, so the row loop reads them with one broadcast load;
+//   * per active row a warp loads its strip segment — one 8-byte entry per lane, idle lanes get
+//     the all-zero entry — straight into registers, 32 rows in flight per warp (a cp.async ring is
+//     kept as the SPMV_STRIP_REGS=0 build: it costs LSU wavefronts twice and was 45 % slower), and
+//     retires it in ONE pass: the entries of one row are distinct columns, so no two lanes meet
+//     in an accumulator (no passes, no votes, no predicates: an idle lane adds 0 to accumulator 0,
+//     columns are stored + 1);
+//   * per-row scalars (segment start, length, x) are fetched lane = row, two to three 32-row
+//     batches ahead, into a small per-warp table, so the row loop reads them with broadcast loads;
 //   * the row ranges of a band are added in range order by strips_reduce_kernel (dependent launch).
 // Deterministic: no atomics at all.
 #include <algorithm>
